@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DDDM hot path on B200 (contract: see repo README / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f32|bf16]
+
+One "step" = one pass of the hot path over one minibatch: the fused energy-score forward+backward
+(K1) on synthetic CIFAR-shaped draws B=128, m=8, D=3072 (BASELINE.json configs[1]).  Inputs are
+resident in HBM for `value`; `e2e` goes through the C-ABI host-buffer session (H2D + kernels + D2H).
+Under torchrun (N > 1) every rank processes its own shard of the global batch (rows are
+independent; no data-path collective; weak scaling) and rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, M, D = 128, 8, 3072
+BETA, LAM, W_BIAS = 0.1, 1.0, 0.0
+METRIC = "energy-score fwd+bwd rows/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def workload_name(dtype: str) -> str:
+    return f"isolated energy-score loss fwd+bwd, synthetic CIFAR-shaped draws B={B} m={M} D={D} {dtype} beta={BETA}"
+
+
+def make_inputs(seed: int, dtype):
+    """SURVEY.md §8(d) 'late' regime (the precision-critical one): x0 in CIFAR range, draws x0 + 0.05 noise."""
+    import torch
+
+    gen = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(B, D, generator=gen).clamp(-1, 1)
+    xh = x0[:, None, :] + 0.05 * torch.randn(B, M, D, generator=gen)
+    t = torch.rand(B, generator=gen)
+    return xh.to(dtype), x0.to(dtype), t
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_port_rate(seconds: float, dtype_name: str):
+    """The reference's CPU path (eager PyTorch + autograd; oracle/torch_port.py) on the host cores:
+    fwd+bwd of the same workload, repeated for about `seconds`; returns (rows/s, iterations, threads)."""
+    import torch
+
+    from oracle import torch_port
+
+    xh, x0, t = make_inputs(0, torch.float32)
+    w = torch_port.sigmoid_weight(t, W_BIAS).mean()
+    torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    best = float("inf")
+    while True:
+        a = time.perf_counter()
+        torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
+        best = min(best, time.perf_counter() - a)
+        n += 1
+        if time.perf_counter() - t0 >= seconds and n >= 3:
+            break
+    mean = (time.perf_counter() - t0) / n
+    return B / mean, n, torch.get_num_threads(), mean, best
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the
+    reference is pure Python/PyTorch and /root/reference is absent on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import torch_port
+
+    xh, x0, t = make_inputs(0, torch.float32)
+    w = torch_port.sigmoid_weight(t, W_BIAS).mean()
+    # bounded: each step is ~0.1-0.3 s of CPU work; cap the whole run at a few minutes
+    steps = max(1, min(args.steps, 200))
+    warmup = max(1, min(args.warmup, 3))
+    for _ in range(warmup):
+        torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name("f32"), "device": "host CPU", "threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} full fwd+bwd passes over the B={B} batch (oracle/torch_port.py, eager "
+                                   f"PyTorch + autograd as in the reference), os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget (rank 0, N=1 only)")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
+    ap.add_argument("--sets", type=int, default=0, help="rotating input sets (0 = enough to exceed 2x L2)")
+    ap.add_argument("--tune", default="", help="comma list key=value for dddm_set_tuning, e.g. energy.cluster=4")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from ddm_b200 import _cabi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _cabi.lib()
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        _cabi.set_tuning(k, int(v))
+
+    tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    esz = 4 if args.dtype == "f32" else 2
+    algo_bytes = (2 * B * M * D + B * D) * esz  # read xhat + x0, write grad
+    nsets = args.sets or max(4, -(-2 * L2_BYTES // algo_bytes) + 1)  # working set > 2x L2: every launch is HBM-cold
+    fn = getattr(L, f"dddm_energy_fused_{args.dtype}")
+    K, W = max(1, args.steps), max(3, args.warmup)
+
+    sets = []
+    for s in range(nsets):
+        xh, x0, t = make_inputs(1000 * rank + s, tdtype)
+        sets.append({"xh": xh.to(dev), "x0": x0.to(dev), "t": t.to(dev), "grad": torch.empty(B, M, D, dtype=tdtype, device=dev),
+                     "out": torch.zeros(4, device=dev), "wsum": torch.empty(1, device=dev),
+                     "ws": torch.zeros(L.dddm_energy_workspace_bytes(B, M), dtype=torch.uint8, device=dev)})
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        for s in sets:  # W = mean_b w(t_b): an input of the isolated loss, computed once outside the timed region
+            _cabi.check(L.dddm_sigmoid_weight_sum_f32(s["t"].data_ptr(), W_BIAS, None, s["wsum"].data_ptr(), B,
+                                                      stream.cuda_stream))
+        if world > 1:  # global-batch weight: one float all-reduce, outside the timed region
+            for s in sets:
+                dist.all_reduce(s["wsum"])
+    stream.synchronize()
+    wscale = 1.0 / (B * world)
+
+    def launch(s, cuda_stream):
+        _cabi.check(fn(s["xh"].data_ptr(), s["x0"].data_ptr(), s["wsum"].data_ptr(), wscale, s["grad"].data_ptr(),
+                       s["out"].data_ptr(), s["ws"].data_ptr(), B, M, D, BETA, LAM, cuda_stream))
+
+    def capture(n):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(n):
+                launch(sets[i % nsets], torch.cuda.current_stream().cuda_stream)
+        return g
+
+    use_graph = not args.no_graph
+    if use_graph:
+        chunk = nsets * max(1, 240 // nsets)
+        g_full = capture(chunk)
+        g_rem = capture(K % chunk) if K % chunk else None
+
+        def run_steps(n):
+            full, rem = divmod(n, chunk)
+            for _ in range(full):
+                g_full.replay()
+            if rem:
+                if n == K and g_rem is not None:
+                    g_rem.replay()
+                else:
+                    for i in range(rem):
+                        launch(sets[i % nsets], stream.cuda_stream)
+    else:
+        def run_steps(n):
+            for i in range(n):
+                launch(sets[i % nsets], stream.cuda_stream)
+
+    launches_before = _cabi.launch_count()
+    with torch.cuda.stream(stream):
+        run_steps(W)
+        run_steps(K)  # extra untimed pass of the whole region: clocks and caches in steady state
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        # repeat the K-step timed region a few times and keep the median: a 5 us kernel makes a single
+        # short region noisy; every repetition times EXACTLY K steps between two events on the launch stream
+        reps = 5 if K * 5e-6 < 0.5 else 1
+        times = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run_steps(K)
+            e1.record(stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e-3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler.stop()
+    elapsed = sorted(times)[len(times) // 2]
+    if world > 1:
+        tmax = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed = float(tmax)
+    del launches_before
+    ms_per_step = 1e3 * elapsed / K
+    value = world * B * K / elapsed
+
+    # ---- e2e: C-ABI host-buffer session (pinned host inputs, H2D + K4 + K1 + D2H of loss & grad every step)
+    e2e_steps = max(3, min(args.e2e_steps, K))
+    host = []
+    for s in range(3):
+        xh, x0, t = make_inputs(5000 + 10 * rank + s, tdtype)
+        host.append((xh.contiguous().pin_memory(), x0.contiguous().pin_memory(), t.contiguous().pin_memory(),
+                     torch.empty(B, M, D, dtype=tdtype).pin_memory(), torch.zeros(4).pin_memory()))
+    sess = L.dddm_session_create(B, M, D, 0 if args.dtype == "f32" else 1, local_rank)
+    if not sess:
+        raise SystemExit(f"dddm_session_create failed: {_cabi.strerror(L.dddm_last_error())}")
+
+    def e2e_run(n):
+        for i in range(n):
+            xh, x0, t, g, o = host[i % 3]
+            _cabi.check(L.dddm_session_enqueue_host(sess, xh.data_ptr(), x0.data_ptr(), t.data_ptr(), W_BIAS, BETA, LAM,
+                                                    g.data_ptr(), o.data_ptr()))
+        _cabi.check(L.dddm_session_wait(sess))
+
+    e2e_run(5)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_run(e2e_steps)
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_dt = float(tmax)
+    L.dddm_session_destroy(sess)
+    e2e_value = world * B * e2e_steps / e2e_dt
+    h2d = (B * M * D + B * D) * esz + B * 4
+    d2h = B * M * D * esz + 16
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = algo_bytes / (elapsed / K) / 1e9
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and args.cpu_seconds > 0:
+            rate, n, threads, mean, best = cpu_port_rate(args.cpu_seconds, args.dtype)
+            cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+                   "sample": f"{n} full fwd+bwd passes over the same B={B},m={M},D={D} fp32 batch with oracle/torch_port.py "
+                             f"(eager PyTorch + autograd, the reference's CPU path), mean {mean * 1e3:.1f} ms, best "
+                             f"{best * 1e3:.1f} ms, os.cpu_count()={os.cpu_count()}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args.dtype), "rows_per_gpu": B, "global_rows": B * world,
+                       "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
+                       "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 2x L2 "
+                                    f"(every launch reads HBM-cold inputs)",
+                       "launch": "CUDA graphs of back-to-back launches, one stream" if use_graph else "python launches",
+                       "timed_region": f"median of {len(times)} repetitions of exactly {K} steps (CUDA events on the "
+                                       f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
+                       "tuning": args.tune or "auto"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                         "frac_of_8TBs_nominal": achieved / 8000.0},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
+                    "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait"},
+            "gpu_launches": K * len(times) // len(times),
+            "clocks": sampler.summary(),
+            "all_region_ms_per_step": [1e3 * x / K for x in times],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,268 @@
+// api.cu — extern "C" entry points of the energy score, argument validation, kernel selection.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "energy.cuh"
+
+namespace dddm {
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+Tuning& tuning() {
+    static Tuning t;
+    return t;
+}
+static thread_local int g_last_error = 0;
+void set_last_error(int e) { g_last_error = e; }
+
+static bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Register-resident plan: m in [2,8]; a row slab of ceil(nvec/cluster) vectors must fit
+// threads * nv with threads <= kRegMaxThreads (256).
+RegPlan plan_reg(int m, int D, int elem_size, bool aligned16, bool is_bwd) {
+    RegPlan r{};
+    r.ok = false;
+    if (m < 2 || m > 8 || D < 1) return r;
+    const int vecw = 16 / elem_size;
+    r.vec = (aligned16 && D % vecw == 0) ? vecw : 1;
+    const long nvec = D / r.vec;
+    const int max_nv = (r.vec > 1 && elem_size == 4) ? 2 : 1;
+    const Tuning& t = tuning();
+    int nv = (t.nv >= 1 && t.nv <= max_nv) ? t.nv : 1;
+    if (is_bwd) {
+        r.cluster = 1;
+        r.nv = nv;
+        long thr = (nvec + nv - 1) / nv;
+        r.threads = (int)(thr >= 256 ? 256 : (thr + 31) / 32 * 32);
+        r.ok = true;
+        return r;
+    }
+    int cluster = 0;
+    if (t.cluster == 1 || t.cluster == 2 || t.cluster == 4 || t.cluster == 8) cluster = t.cluster;
+    if (cluster == 0) {
+        // auto: smallest power-of-two cluster whose slab fits 128 threads, capped at 8 CTAs per row
+        cluster = 1;
+        while (cluster < 8 && (nvec + cluster - 1) / cluster > 128L * nv) cluster *= 2;
+    }
+    long per_cta = (nvec + cluster - 1) / cluster;
+    if (per_cta > 256L * nv && t.nv == 0 && max_nv == 2) nv = 2;
+    if (per_cta > 256L * nv) return r;  // slab too wide for the register tile: use the smem-tile kernel
+    r.cluster = cluster;
+    r.nv = nv;
+    long thr = (per_cta + nv - 1) / nv;
+    r.threads = (int)((thr + 31) / 32 * 32);
+    if (r.threads < 32) r.threads = 32;
+    r.ok = true;
+    return r;
+}
+
+static int validate(const void* xhat, const void* x0, const void* out, const void* ws, int B, int m, int D) {
+    if (!xhat || !x0 || !out || !ws) return DDDM_ERR_NULL_POINTER;
+    if (m < 2) return DDDM_ERR_BAD_SHAPE;  // training.py:57-58
+    if (B < 1 || D < 1 || B > 65535) return DDDM_ERR_BAD_SHAPE;
+    if (!is_aligned16(ws)) return DDDM_ERR_BAD_ALIGNMENT;
+    return DDDM_OK;
+}
+
+template <typename T>
+static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
+    auto* ws = static_cast<EnergyWorkspace*>(workspace);
+    p.ticket = &ws->ticket;
+    p.row_partials = reinterpret_cast<float*>(ws + 1);
+    const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
+                    ((long)p.D * (long)sizeof(T)) % 16 == 0;
+    const int variant = tuning().variant;
+    if (variant != 2) {
+        RegPlan plan = plan_reg(p.m, p.D, (int)sizeof(T), al, false);
+        if (plan.ok) return launch_energy_reg<T>(p, plan, stream);
+        if (variant == 1) return DDDM_ERR_UNSUPPORTED;
+    }
+    TilePlan tp = plan_tile(p.m, p.D, (int)sizeof(T), al);
+    if (!tp.ok) return DDDM_ERR_UNSUPPORTED;
+    return launch_energy_tile<T>(p, tp, stream);
+}
+
+template <typename T>
+static int energy_fused(const T* xhat, const T* x0, const float* weight_dev, float weight_scale, T* grad, float* out,
+                        void* workspace, int B, int m, int D, float beta, float lam, cudaStream_t stream) {
+    int st = validate(xhat, x0, out, workspace, B, m, D);
+    if (st != DDDM_OK) return st;
+    if (!weight_dev) return DDDM_ERR_NULL_POINTER;
+    EnergyParams p{};
+    p.xhat = xhat;
+    p.x0 = x0;
+    p.grad_xhat = grad;
+    p.weight_dev = weight_dev;
+    p.weight_scale = weight_scale;
+    p.out = out;
+    p.B = B;
+    p.m = m;
+    p.D = D;
+    p.lam = lam;
+    p.pw = make_pow_spec(beta);
+    p.mode = kModeLoss;
+    return run_forward<T>(p, workspace, stream);
+}
+
+template <typename T>
+static int energy_terms_fwd(const T* xhat, const T* x0, float* dist, float* out, void* workspace, int B, int m, int D,
+                            float beta, cudaStream_t stream) {
+    int st = validate(xhat, x0, out, workspace, B, m, D);
+    if (st != DDDM_OK) return st;
+    EnergyParams p{};
+    p.xhat = xhat;
+    p.x0 = x0;
+    p.dist = dist;
+    p.out = out;
+    p.B = B;
+    p.m = m;
+    p.D = D;
+    p.lam = 0.f;
+    p.pw = make_pow_spec(beta);
+    p.mode = kModeTerms;
+    return run_forward<T>(p, workspace, stream);
+}
+
+template <typename T>
+static int energy_terms_bwd(const T* xhat, const T* x0, const float* dist, const float* g_conf, const float* g_inter,
+                            T* grad_xhat, T* grad_x0, int B, int m, int D, float beta, cudaStream_t stream) {
+    if (!xhat || !x0 || !dist || !g_conf || !g_inter || !grad_xhat) return DDDM_ERR_NULL_POINTER;
+    if (m < 2 || B < 1 || D < 1 || B > 65535) return DDDM_ERR_BAD_SHAPE;
+    EnergyParams p{};
+    p.xhat = xhat;
+    p.x0 = x0;
+    p.dist = const_cast<float*>(dist);
+    p.g_conf = g_conf;
+    p.g_inter = g_inter;
+    p.grad_xhat = grad_xhat;
+    p.grad_x0 = grad_x0;
+    p.B = B;
+    p.m = m;
+    p.D = D;
+    p.pw = make_pow_spec(beta);
+    p.mode = kModeTerms;
+    const bool al = is_aligned16(xhat) && is_aligned16(x0) && is_aligned16(grad_xhat) &&
+                    (!grad_x0 || is_aligned16(grad_x0)) && ((long)D * (long)sizeof(T)) % 16 == 0;
+    if (tuning().variant != 2) {
+        RegPlan plan = plan_reg(m, D, (int)sizeof(T), al, true);
+        if (plan.ok) return launch_energy_bwd_reg<T>(p, plan, stream);
+    }
+    TilePlan tp = plan_tile(m, D, (int)sizeof(T), al);
+    if (!tp.ok) return DDDM_ERR_UNSUPPORTED;
+    return launch_energy_bwd_tile<T>(p, tp, stream);
+}
+
+}  // namespace dddm
+
+using namespace dddm;
+using bf16 = __nv_bfloat16;
+
+extern "C" {
+
+int dddm_abi_version(void) { return DDDM_ABI_VERSION; }
+
+const char* dddm_strerror(int status) {
+    switch (status) {
+        case DDDM_OK: return "ok";
+        case DDDM_ERR_NULL_POINTER: return "dddm: required pointer is NULL";
+        case DDDM_ERR_BAD_SHAPE: return "dddm: bad shape (need B >= 1, D >= 1, m >= 2 to form interaction pairs)";
+        case DDDM_ERR_BAD_ALIGNMENT: return "dddm: workspace must be 16-byte aligned";
+        case DDDM_ERR_UNSUPPORTED: return "dddm: no kernel variant supports this shape";
+        case DDDM_ERR_BAD_ARGUMENT: return "dddm: bad argument";
+        case DDDM_ERR_NO_DEVICE: return "dddm: no CUDA device";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "dddm: unknown status";
+}
+
+size_t dddm_energy_workspace_bytes(int B, int m) {
+    (void)m;
+    if (B < 1) B = 1;
+    return sizeof(EnergyWorkspace) + (size_t)B * 2 * sizeof(float);
+}
+size_t dddm_energy_dist_per_row(int m) { return m < 2 ? 0 : (size_t)m + (size_t)m * (m - 1) / 2; }
+
+int dddm_energy_fused_f32(const float* xhat, const float* x0, const float* weight_dev, float weight_scale,
+                          float* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta, float lam,
+                          dddm_stream_t stream) {
+    return energy_fused<float>(xhat, x0, weight_dev, weight_scale, grad_xhat, out, workspace, B, m, D, beta, lam,
+                               (cudaStream_t)stream);
+}
+int dddm_energy_fused_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* weight_dev, float weight_scale,
+                           dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
+                           float lam, dddm_stream_t stream) {
+    return energy_fused<bf16>((const bf16*)xhat, (const bf16*)x0, weight_dev, weight_scale, (bf16*)grad_xhat, out,
+                              workspace, B, m, D, beta, lam, (cudaStream_t)stream);
+}
+int dddm_energy_terms_fwd_f32(const float* xhat, const float* x0, float* dist, float* out, void* workspace, int B,
+                              int m, int D, float beta, dddm_stream_t stream) {
+    return energy_terms_fwd<float>(xhat, x0, dist, out, workspace, B, m, D, beta, (cudaStream_t)stream);
+}
+int dddm_energy_terms_fwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, float* dist, float* out, void* workspace,
+                               int B, int m, int D, float beta, dddm_stream_t stream) {
+    return energy_terms_fwd<bf16>((const bf16*)xhat, (const bf16*)x0, dist, out, workspace, B, m, D, beta,
+                                  (cudaStream_t)stream);
+}
+int dddm_energy_terms_bwd_f32(const float* xhat, const float* x0, const float* dist, const float* g_conf,
+                              const float* g_inter, float* grad_xhat, float* grad_x0, int B, int m, int D, float beta,
+                              dddm_stream_t stream) {
+    return energy_terms_bwd<float>(xhat, x0, dist, g_conf, g_inter, grad_xhat, grad_x0, B, m, D, beta,
+                                   (cudaStream_t)stream);
+}
+int dddm_energy_terms_bwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* dist, const float* g_conf,
+                               const float* g_inter, dddm_bf16* grad_xhat, dddm_bf16* grad_x0, int B, int m, int D,
+                               float beta, dddm_stream_t stream) {
+    return energy_terms_bwd<bf16>((const bf16*)xhat, (const bf16*)x0, dist, g_conf, g_inter, (bf16*)grad_xhat,
+                                  (bf16*)grad_x0, B, m, D, beta, (cudaStream_t)stream);
+}
+
+int dddm_set_tuning(const char* key, int value) {
+    if (!key) return DDDM_ERR_NULL_POINTER;
+    Tuning& t = tuning();
+    if (!strcmp(key, "energy.cluster")) t.cluster = value;
+    else if (!strcmp(key, "energy.nv")) t.nv = value;
+    else if (!strcmp(key, "energy.variant")) t.variant = value;
+    else if (!strcmp(key, "energy.pdl")) t.pdl = value;
+    else return DDDM_ERR_BAD_ARGUMENT;
+    return DDDM_OK;
+}
+int dddm_get_tuning(const char* key) {
+    if (!key) return DDDM_ERR_NULL_POINTER;
+    const Tuning& t = tuning();
+    if (!strcmp(key, "energy.cluster")) return t.cluster;
+    if (!strcmp(key, "energy.nv")) return t.nv;
+    if (!strcmp(key, "energy.variant")) return t.variant;
+    if (!strcmp(key, "energy.pdl")) return t.pdl;
+    return DDDM_ERR_BAD_ARGUMENT;
+}
+unsigned long long dddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) {
+    (void)B;
+    if (!buf || buflen < 1) return DDDM_ERR_NULL_POINTER;
+    const int es = dtype == 1 ? 2 : 4;
+    const bool al = ((long)D * es) % 16 == 0;
+    int n;
+    if (tuning().variant != 2) {
+        RegPlan r = plan_reg(m, D, es, al, false);
+        if (r.ok) {
+            n = snprintf(buf, buflen, "reg<%s,M=%d,VEC=%d,NV=%d> cluster=%d threads=%d", dtype == 1 ? "bf16" : "f32", m,
+                         r.vec, r.nv, r.cluster, r.threads);
+            return n;
+        }
+    }
+    TilePlan t = plan_tile(m, D, es, al);
+    if (t.ok)
+        n = snprintf(buf, buflen, "tile<%s,m=%d> cluster=%d threads=%d chunk=%d slab=%d smem=%zu %s",
+                     dtype == 1 ? "bf16" : "f32", m, t.cluster, t.threads, t.chunk_cols, t.slab_cols, t.smem_bytes,
+                     t.bulk ? "tma-bulk" : "ldg");
+    else
+        n = snprintf(buf, buflen, "unsupported");
+    return n;
+}
+
+int dddm_last_error(void) { return g_last_error; }
+
+}  // extern "C"

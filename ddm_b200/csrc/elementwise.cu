@@ -1,0 +1,280 @@
+// elementwise.cu — the HBM-bound elementwise kernels around the energy score.
+//   K2  forward marginal + m-fold expansion   (dddm/schedules.py:17-25, dddm/training.py:70)
+//   K3  Gaussian bridge + Algorithm-2 update  (dddm/schedules.py:28-78, dddm/sampling.py:29-31)
+//   K4  logistic weight w(t) and its batch sum (dddm/losses.py:28-35, dddm/training.py:84)
+//   scale-in-place (hand-off of the pre-multiplied gradient of K1 to autograd)
+// All are pure streaming kernels: 16-byte vector loads/stores, grids sized as a multiple of the
+// SM count, no shared-memory staging (nothing is reused).
+#include "common.cuh"
+
+namespace dddm {
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <typename T>
+static bool aligned16(const T* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// ---- K2 ------------------------------------------------------------------------------------
+// grid: (column tiles, rows).  Each thread owns one VEC-wide column group of one row b, computes
+// xt once and writes it to xt (optional) and to the m expanded rows b*m .. b*m+m-1.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+forward_marginal_expand_kernel(const T* __restrict__ x0, const float* __restrict__ t, const T* __restrict__ eps,
+                               T* __restrict__ xt, T* __restrict__ xt_rep, int m, long D) {
+    const long nvec = D / VEC;
+    const int b = blockIdx.y;
+    const float tb = t[b];
+    const float ab = 1.0f - tb;  // alpha_sigma, schedules.py:5-14
+    const T* x0r = x0 + (long)b * D;
+    const T* er = eps + (long)b * D;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+        float a[VEC], e[VEC], o[VEC];
+        load_pack<T, VEC>(x0r, v * VEC, a);
+        load_pack<T, VEC>(er, v * VEC, e);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = __fadd_rn(__fmul_rn(ab, a[k]), __fmul_rn(tb, e[k]));  // no FMA: matches eager
+        if (xt != nullptr) store_pack<T, VEC>(xt + (long)b * D, v * VEC, o);
+        if (xt_rep != nullptr) {
+            T* base = xt_rep + (long)b * m * D;
+            for (int i = 0; i < m; ++i) store_pack<T, VEC>(base + (long)i * D, v * VEC, o);
+        }
+    }
+}
+
+template <typename T>
+static int forward_marginal_expand(const T* x0, const float* t, const T* eps, T* xt, T* xt_rep, int B, int m, long D,
+                                   cudaStream_t stream) {
+    if (!x0 || !t || !eps || (!xt && !xt_rep)) return DDDM_ERR_NULL_POINTER;
+    if (B < 0 || D < 0 || (xt_rep && m < 1) || B > 65535 * 32) return DDDM_ERR_BAD_SHAPE;
+    if (B == 0 || D == 0) return DDDM_OK;
+    constexpr int V = Elem<T>::kVec;
+    const bool vec = (D % V == 0) && aligned16(x0) && aligned16(eps) && (!xt || aligned16(xt)) &&
+                     (!xt_rep || aligned16(xt_rep));
+    const long nvec = vec ? D / V : D;
+    const int threads = nvec >= 256 ? 256 : (int)((nvec + 31) / 32 * 32);
+    long tiles = (nvec + threads - 1) / threads;
+    // enough CTAs to fill the machine, no more than ~8 waves of work items per CTA column
+    const long max_tiles = ((long)num_sms() * 8 + B - 1) / B;
+    if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
+    if (B > 65535) return DDDM_ERR_BAD_SHAPE;
+    dim3 grid((unsigned)tiles, (unsigned)B);
+    if (vec)
+        forward_marginal_expand_kernel<T, V><<<grid, threads, 0, stream>>>(x0, t, eps, xt, xt_rep, m, D);
+    else
+        forward_marginal_expand_kernel<T, 1><<<grid, threads, 0, stream>>>(x0, t, eps, xt, xt_rep, m, D);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---- K4 ------------------------------------------------------------------------------------
+__device__ __forceinline__ float logistic_weight(float t, float bias) {
+    const float a = 1.0f - t;
+    const float ratio = __fdiv_rn(a * a, t * t + kWeightEps);
+    const float z = logf(ratio + kWeightEps) - bias;
+    return 1.0f / (1.0f + expf(-z));
+}
+
+// Single CTA (B is a minibatch size): per-thread strided partial sums, fixed-shape tree -> deterministic.
+__global__ void __launch_bounds__(1024)
+sigmoid_weight_sum_kernel(const float* __restrict__ t, float bias, float* __restrict__ w, float* __restrict__ w_sum,
+                          int B) {
+    __shared__ float s_part[32];
+    float acc = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float wb = logistic_weight(t[b], bias);
+        if (w != nullptr) w[b] = wb;
+        acc += wb;
+    }
+    if (w_sum == nullptr) return;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) w_sum[0] = v;
+    }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------
+struct BridgeCoef {
+    float c_xt, c_x0, std;
+};
+// schedules.py:45-77 in fp32, operation for operation (so the scalar-coefficient form reproduces
+// the reference's eager result; SURVEY.md §8c "bit-exactly on CPU").
+// e2 = eps_churn^2 and ome2 = 1 - eps_churn^2 are formed in double on the host and rounded once,
+// exactly like the Python scalars the reference multiplies its fp32 tensors with.
+__device__ __forceinline__ BridgeCoef bridge_coef(float s, float t, float e2, float ome2) {
+    const float a_s = 1.0f - s, a_t = 1.0f - t;
+    const float ratio = __fdiv_rn(s, t + kBridgeEps);
+    const float alpha_ratio = __fdiv_rn(a_t, a_s + kBridgeEps);
+    const float r11 = __fmul_rn(alpha_ratio, ratio);
+    const float r12 = __fmul_rn(alpha_ratio, __fmul_rn(ratio, ratio));
+    BridgeCoef c;
+    c.c_xt = __fadd_rn(__fmul_rn(e2, r12), __fmul_rn(ome2, ratio));
+    c.c_x0 = __fmul_rn(a_s, __fsub_rn(__fsub_rn(1.0f, __fmul_rn(e2, r12)), __fmul_rn(ome2, r11)));
+    const float inner = __fadd_rn(__fmul_rn(e2, r11), ome2);
+    const float var = __fmul_rn(__fmul_rn(s, s), fmaxf(__fsub_rn(1.0f, __fmul_rn(inner, inner)), 0.0f));
+    c.std = sqrtf(fmaxf(var, 0.0f));
+    return c;
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bridge_step_kernel(T* __restrict__ x_out, const T* __restrict__ x, const T* __restrict__ xhat0,
+                   const T* __restrict__ z, const float* __restrict__ s, const float* __restrict__ t,
+                   int st_is_vector, float e2, float ome2, T* __restrict__ mu_out, float* __restrict__ std_out, long N,
+                   long D) {
+    const long nvec = D / VEC;
+    for (long n = blockIdx.y; n < N; n += gridDim.y) {
+        const BridgeCoef c = st_is_vector ? bridge_coef(s[n], t[n], e2, ome2) : bridge_coef(s[0], t[0], e2, ome2);
+        if (std_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (st_is_vector || n == 0)) std_out[n] = c.std;
+        const long base = n * D;
+        for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+            float xv[VEC], hv[VEC], zv[VEC], mu[VEC], o[VEC];
+            load_pack<T, VEC>(x + base, v * VEC, xv);
+            load_pack<T, VEC>(xhat0 + base, v * VEC, hv);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) mu[k] = __fadd_rn(__fmul_rn(c.c_xt, xv[k]), __fmul_rn(c.c_x0, hv[k]));
+            if (mu_out != nullptr) store_pack<T, VEC>(mu_out + base, v * VEC, mu);
+            if (x_out != nullptr) {
+                if (z != nullptr) {
+                    load_pack<T, VEC>(z + base, v * VEC, zv);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) o[k] = __fadd_rn(mu[k], __fmul_rn(c.std, zv[k]));
+                    store_pack<T, VEC>(x_out + base, v * VEC, o);
+                } else {
+                    store_pack<T, VEC>(x_out + base, v * VEC, mu);
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const float* s, const float* t,
+                       int st_is_vector, double eps_churn, T* mu_out, float* std_out, long N, long D,
+                       cudaStream_t stream) {
+    if (!x || !xhat0 || !s || !t || (!x_out && !mu_out)) return DDDM_ERR_NULL_POINTER;
+    if (N < 0 || D < 0) return DDDM_ERR_BAD_SHAPE;
+    if (N == 0 || D == 0) return DDDM_OK;
+    constexpr int V = Elem<T>::kVec;
+    const bool vec = (D % V == 0) && aligned16(x) && aligned16(xhat0) && (!z || aligned16(z)) &&
+                     (!x_out || aligned16(x_out)) && (!mu_out || aligned16(mu_out));
+    const long nvec = vec ? D / V : D;
+    const int threads = nvec >= 256 ? 256 : (int)((nvec + 31) / 32 * 32);
+    long tiles = (nvec + threads - 1) / threads;
+    const long rows = N < 65535 ? N : 65535;
+    const long max_tiles = ((long)num_sms() * 8 + rows - 1) / rows;
+    if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
+    dim3 grid((unsigned)tiles, (unsigned)rows);
+    const float e2 = (float)(eps_churn * eps_churn), ome2 = (float)(1.0 - eps_churn * eps_churn);
+    if (vec)
+        bridge_step_kernel<T, V><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
+                                                                mu_out, std_out, N, D);
+    else
+        bridge_step_kernel<T, 1><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
+                                                                mu_out, std_out, N, D);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---- scale in place ------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) scale_inplace_kernel(T* __restrict__ y, const float* __restrict__ scale, size_t n) {
+    const float sc = scale[0];
+    if (sc == 1.0f) return;  // upstream gradient of exactly 1: the buffer already holds dloss/dxhat
+    const size_t nvec = n / VEC;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        float a[VEC];
+        load_pack<T, VEC>(y, (long)(v * VEC), a);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a[k] *= sc;
+        store_pack<T, VEC>(y, (long)(v * VEC), a);
+    }
+    // tail (n not a multiple of VEC)
+    for (size_t i = nvec * VEC + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = Elem<T>::from_float(Elem<T>::to_float(y[i]) * sc);
+}
+
+template <typename T>
+static int scale_inplace(T* y, const float* scale, size_t n, cudaStream_t stream) {
+    if (!y || !scale) return DDDM_ERR_NULL_POINTER;
+    if (n == 0) return DDDM_OK;
+    constexpr int V = Elem<T>::kVec;
+    const bool vec = aligned16(y);
+    const size_t work = vec ? (n + V - 1) / V : n;
+    size_t blocks = (work + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (vec)
+        scale_inplace_kernel<T, V><<<(unsigned)blocks, 256, 0, stream>>>(y, scale, n);
+    else
+        scale_inplace_kernel<T, 1><<<(unsigned)blocks, 256, 0, stream>>>(y, scale, n);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dddm
+
+using namespace dddm;
+
+extern "C" {
+
+int dddm_forward_marginal_expand_f32(const float* x0, const float* t, const float* eps, float* xt, float* xt_rep,
+                                     int B, int m, long D, dddm_stream_t stream) {
+    return forward_marginal_expand<float>(x0, t, eps, xt, xt_rep, B, m, D, (cudaStream_t)stream);
+}
+int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, dddm_bf16* xt,
+                                      dddm_bf16* xt_rep, int B, int m, long D, dddm_stream_t stream) {
+    return forward_marginal_expand<__nv_bfloat16>((const __nv_bfloat16*)x0, t, (const __nv_bfloat16*)eps,
+                                                  (__nv_bfloat16*)xt, (__nv_bfloat16*)xt_rep, B, m, D,
+                                                  (cudaStream_t)stream);
+}
+
+int dddm_sigmoid_weight_sum_f32(const float* t, float bias, float* w, float* w_sum, int B, dddm_stream_t stream) {
+    if (!t || (!w && !w_sum)) return DDDM_ERR_NULL_POINTER;
+    if (B < 0) return DDDM_ERR_BAD_SHAPE;
+    if (B == 0) {
+        if (w_sum) return (int)cudaMemsetAsync(w_sum, 0, sizeof(float), (cudaStream_t)stream);
+        return DDDM_OK;
+    }
+    int threads = B >= 1024 ? 1024 : (B + 31) / 32 * 32;
+    sigmoid_weight_sum_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(t, bias, w, w_sum, B);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int dddm_bridge_step_f32(float* x_out, const float* x, const float* xhat0, const float* z, const float* s,
+                         const float* t, int st_is_vector, double eps_churn, float* mu_out, float* std_out, long N,
+                         long D, dddm_stream_t stream) {
+    return bridge_step<float>(x_out, x, xhat0, z, s, t, st_is_vector, eps_churn, mu_out, std_out, N, D,
+                              (cudaStream_t)stream);
+}
+int dddm_bridge_step_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16* xhat0, const dddm_bf16* z,
+                          const float* s, const float* t, int st_is_vector, double eps_churn, dddm_bf16* mu_out,
+                          float* std_out, long N, long D, dddm_stream_t stream) {
+    return bridge_step<__nv_bfloat16>((__nv_bfloat16*)x_out, (const __nv_bfloat16*)x, (const __nv_bfloat16*)xhat0,
+                                      (const __nv_bfloat16*)z, s, t, st_is_vector, eps_churn, (__nv_bfloat16*)mu_out,
+                                      std_out, N, D, (cudaStream_t)stream);
+}
+
+int dddm_scale_inplace_f32(float* y, const float* scale, size_t n, dddm_stream_t stream) {
+    return scale_inplace<float>(y, scale, n, (cudaStream_t)stream);
+}
+int dddm_scale_inplace_bf16(dddm_bf16* y, const float* scale, size_t n, dddm_stream_t stream) {
+    return scale_inplace<__nv_bfloat16>((__nv_bfloat16*)y, scale, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

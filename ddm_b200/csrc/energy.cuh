@@ -1,0 +1,118 @@
+// energy.cuh — shared declarations of the energy-score kernels (K1 fused, K1b split pair).
+#pragma once
+
+#include "common.cuh"
+
+namespace dddm {
+
+// What one energy launch computes.
+enum EnergyMode : int {
+    kModeLoss = 0,   // training.py:84-85: out = {loss, conf, inter, W}; grad (optional) = dloss/dxhat
+    kModeTerms = 1,  // losses.py:5-25:    out = {conf, inter}; dist saved for the backward
+};
+
+struct EnergyParams {
+    const void* xhat;  // [B,m,D]
+    const void* x0;    // [B,D]
+    void* grad_xhat;   // [B,m,D] or null
+    void* grad_x0;     // [B,D] or null (backward kernel only)
+    const float* weight_dev;  // kModeLoss: W = weight_dev[0] * weight_scale
+    float weight_scale;
+    const float* g_conf;   // backward kernel: upstream gradients (device scalars)
+    const float* g_inter;
+    float* dist;           // [B, m + m(m-1)/2] saved squared distances (written in kModeTerms, read by bwd)
+    float* out;            // device scalars
+    float* row_partials;   // [B][2] workspace
+    unsigned* ticket;      // arrival counter (workspace)
+    int B, m, D;
+    float lam;
+    PowSpec pw;
+    int mode;
+};
+
+struct EnergyWorkspace {  // layout of the caller-provided workspace
+    unsigned ticket;
+    unsigned pad[3];
+    // float row_partials[B][2] follows
+};
+
+// Launch plan of the register-resident kernels for a shape (energy_reg.cu).
+struct RegPlan {
+    bool ok;
+    int vec;      // elements per thread vector (1 or 16 bytes worth)
+    int nv;       // vectors per thread
+    int cluster;  // CTAs per row
+    int threads;
+};
+RegPlan plan_reg(int m, int D, int elem_size, bool aligned16, bool is_bwd);
+
+template <typename T>
+int launch_energy_reg(const EnergyParams& p, const RegPlan& plan, cudaStream_t stream);
+template <typename T>
+int launch_energy_bwd_reg(const EnergyParams& p, const RegPlan& plan, cudaStream_t stream);
+
+// Shared-memory tile kernels for any m (energy_tile.cu).
+struct TilePlan {
+    bool ok;
+    int cluster;
+    int threads;
+    int chunk_cols;    // columns per staged chunk
+    int slab_cols;     // columns per CTA
+    size_t smem_bytes;
+    bool bulk;         // rows are 16-byte aligned: stage with cp.async.bulk (TMA)
+};
+TilePlan plan_tile(int m, int D, int elem_size, bool aligned16);
+template <typename T>
+int launch_energy_tile(const EnergyParams& p, const TilePlan& plan, cudaStream_t stream);
+template <typename T>
+int launch_energy_bwd_tile(const EnergyParams& p, const TilePlan& plan, cudaStream_t stream);
+
+// ---- deterministic cross-row reduction, executed by the last arriving row ------------------
+// Called by ONE warp of the CTA that owns row b after its per-row sums are known.
+__device__ __forceinline__ void finish_row(const EnergyParams& p, int b, float conf_row, float inter_row, float W,
+                                           int lane) {
+    unsigned old = 0;
+    if (lane == 0) {
+        reinterpret_cast<float2*>(p.row_partials)[b] = make_float2(conf_row, inter_row);
+        __threadfence();
+        old = atomicAdd(p.ticket, 1u);
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != (unsigned)(p.B - 1)) return;
+    // last row: every row's partials are visible after the fence; sum them in a fixed order
+    __threadfence();
+    float c = 0.f, i = 0.f;
+    for (int r = lane; r < p.B; r += 32) {
+        float2 v = __ldcg(reinterpret_cast<const float2*>(p.row_partials) + r);
+        c += v.x;
+        i += v.y;
+    }
+    c = warp_sum(c);
+    i = warp_sum(i);
+    if (lane == 0) {
+        const float conf = c / ((float)p.B * (float)p.m);
+        const float inter = i / ((float)p.B * (float)p.m * (float)(p.m - 1));
+        if (p.mode == kModeLoss) {
+            const float cl = p.lam / (2.0f * (float)(p.m - 1));
+            p.out[0] = W * (conf - cl * inter);
+            p.out[1] = conf;
+            p.out[2] = inter;
+            p.out[3] = W;
+        } else {
+            p.out[0] = conf;
+            p.out[1] = inter;
+        }
+        *p.ticket = 0u;  // leave the workspace reusable
+    }
+}
+
+// Coefficients multiplying (x_i - x0) and (x_i - x_j) in the gradient, given upstream (gc, gi):
+//   d/dxhat_i [gc*conf + gi*inter] = sum_k coef_k * difference_k      (SURVEY.md §8a closed form)
+__device__ __forceinline__ float conf_coef(float d2, float gc, const EnergyParams& p) {
+    return 2.0f * gc / ((float)p.B * (float)p.m) * pow_deriv(d2, p.pw);
+}
+__device__ __forceinline__ float pair_coef(float d2, float gi, const EnergyParams& p) {
+    return 4.0f * gi / ((float)p.B * (float)p.m * (float)(p.m - 1)) * pow_deriv(d2, p.pw);
+}
+
+}  // namespace dddm

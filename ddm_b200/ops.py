@@ -1,0 +1,334 @@
+"""PyTorch custom ops over the C ABI (``include/dddm_b200.h``).
+
+torch is plumbing here: it owns the device memory and the stream; every op body is one call
+into ``libdddm_b200.so`` with raw device pointers.  All ops are CUDA-only and raise if handed
+CPU tensors — there is no eager fallback.  ``register_fake`` gives shape/dtype propagation so
+that DDP / ``torch.compile`` tracing does not break, ``register_autograd`` wires the fused and
+split energy-score gradients into autograd.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+
+_SUFFIX = {torch.float32: "f32", torch.bfloat16: "bf16"}
+
+
+def _suffix(t: Tensor) -> str:
+    try:
+        return _SUFFIX[t.dtype]
+    except KeyError:
+        raise TypeError(f"ddm_b200 kernels support float32 and bfloat16, got {t.dtype}") from None
+
+
+def _require_cuda(*tensors: Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ddm_b200 is CUDA-only (sm_100a kernels, no CPU fallback): got a tensor on "
+                               f"{t.device}; move inputs to a CUDA device")
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+_workspaces: dict = {}
+
+
+def _workspace(ref: Tensor, B: int, m: int) -> Tensor:
+    """Zero-initialised energy workspace, one per (device, stream): launches on one stream are ordered."""
+    key = (ref.device.index, _stream(ref))
+    need = _cabi.lib().dddm_energy_workspace_bytes(B, m)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 4096), dtype=torch.uint8, device=ref.device)
+        _workspaces[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------------------------
+# K1: fused energy-score loss forward + backward  (dddm/training.py:77-85, dddm/losses.py:5-25)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("ddm_b200::energy_fused", mutates_args=())
+def energy_fused(xhat: Tensor, x0: Tensor, weight: Tensor, weight_scale: float, beta: float, lam: float,
+                 want_grad: bool) -> Tuple[Tensor, Tensor]:
+    """Returns (out[4] = {loss, conf, inter, W} fp32, dloss/dxhat or an empty tensor)."""
+    _require_cuda(xhat, x0, weight)
+    if xhat.dim() != 3 or x0.dim() != 2 or x0.shape[0] != xhat.shape[0] or x0.shape[1] != xhat.shape[2]:
+        raise ValueError(f"expected xhat [B,m,D] and x0 [B,D], got {tuple(xhat.shape)} and {tuple(x0.shape)}")
+    if x0.dtype != xhat.dtype:
+        raise TypeError("xhat and x0 must have the same dtype")
+    sfx = _suffix(xhat)
+    xhat, x0 = xhat.contiguous(), x0.contiguous()
+    weight = weight.reshape(-1)[:1].float().contiguous()
+    B, m, D = xhat.shape
+    out = torch.empty(4, dtype=torch.float32, device=xhat.device)
+    grad = torch.empty_like(xhat) if want_grad else torch.empty(0, dtype=xhat.dtype, device=xhat.device)
+    with torch.cuda.device(xhat.device):
+        ws = _workspace(xhat, B, m)
+        fn = getattr(_cabi.lib(), f"dddm_energy_fused_{sfx}")
+        _cabi.check(fn(_ptr(xhat), _ptr(x0), _ptr(weight), float(weight_scale), _ptr(grad) if want_grad else None,
+                       _ptr(out), _ptr(ws), B, m, D, float(beta), float(lam), _stream(xhat)))
+    return out, grad
+
+
+@energy_fused.register_fake
+def _(xhat, x0, weight, weight_scale, beta, lam, want_grad):
+    out = xhat.new_empty(4, dtype=torch.float32)
+    return out, (torch.empty_like(xhat) if want_grad else xhat.new_empty(0))
+
+
+@torch.library.custom_op("ddm_b200::scale_", mutates_args=("y",))
+def scale_(y: Tensor, scale: Tensor) -> None:
+    """y *= scale[0] unless scale[0] == 1 (tested on the device; no host synchronisation)."""
+    _require_cuda(y, scale)
+    sfx = _suffix(y)
+    if not y.is_contiguous():
+        raise ValueError("scale_ needs a contiguous tensor")
+    scale = scale.reshape(-1)[:1].float().contiguous()
+    with torch.cuda.device(y.device):
+        fn = getattr(_cabi.lib(), f"dddm_scale_inplace_{sfx}")
+        _cabi.check(fn(_ptr(y), _ptr(scale), y.numel(), _stream(y)))
+
+
+def _energy_fused_setup(ctx, inputs, output):
+    ctx.want_grad = inputs[6]
+    ctx.save_for_backward(output[1])
+    ctx.consumed = False
+
+
+def _energy_fused_backward(ctx, g_out, g_grad):
+    if not ctx.want_grad:
+        raise RuntimeError("energy_fused was called with want_grad=False but its output is being differentiated")
+    if ctx.consumed:
+        raise RuntimeError("the fused energy-score gradient buffer was already consumed by a previous backward(); "
+                           "use generalized_energy_terms (split kernels) when you need retain_graph=True")
+    (grad,) = ctx.saved_tensors
+    ctx.consumed = True
+    # the kernel emitted dloss/dxhat assuming an upstream gradient of 1 for out[0] (the loss); only
+    # out[0] is differentiable — conf/inter/W in out[1:] are logging values.
+    scale_(grad, g_out[:1])
+    return grad, None, None, None, None, None, None
+
+
+energy_fused.register_autograd(_energy_fused_backward, setup_context=_energy_fused_setup)
+
+
+# --------------------------------------------------------------------------------------------
+# K1b: generalized_energy_terms forward / backward pair  (dddm/losses.py:5-25)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("ddm_b200::energy_terms_fwd", mutates_args=())
+def energy_terms_fwd(xhat: Tensor, x0: Tensor, beta: float) -> Tuple[Tensor, Tensor]:
+    """Returns (out[2] = {conf, inter} fp32, dist [B, m + m(m-1)/2] fp32 squared distances)."""
+    _require_cuda(xhat, x0)
+    if xhat.dim() != 3 or x0.dim() != 2 or x0.shape[0] != xhat.shape[0] or x0.shape[1] != xhat.shape[2]:
+        raise ValueError(f"expected xhat [B,m,D] and x0 [B,D], got {tuple(xhat.shape)} and {tuple(x0.shape)}")
+    if x0.dtype != xhat.dtype:
+        raise TypeError("xhat and x0 must have the same dtype")
+    sfx = _suffix(xhat)
+    xhat, x0 = xhat.contiguous(), x0.contiguous()
+    B, m, D = xhat.shape
+    out = torch.empty(2, dtype=torch.float32, device=xhat.device)
+    dist = torch.empty((B, m + m * (m - 1) // 2), dtype=torch.float32, device=xhat.device)
+    with torch.cuda.device(xhat.device):
+        ws = _workspace(xhat, B, m)
+        fn = getattr(_cabi.lib(), f"dddm_energy_terms_fwd_{sfx}")
+        _cabi.check(fn(_ptr(xhat), _ptr(x0), _ptr(dist), _ptr(out), _ptr(ws), B, m, D, float(beta), _stream(xhat)))
+    return out, dist
+
+
+@energy_terms_fwd.register_fake
+def _(xhat, x0, beta):
+    B, m, _ = xhat.shape
+    return xhat.new_empty(2, dtype=torch.float32), xhat.new_empty((B, m + m * (m - 1) // 2), dtype=torch.float32)
+
+
+@torch.library.custom_op("ddm_b200::energy_terms_bwd", mutates_args=())
+def energy_terms_bwd(xhat: Tensor, x0: Tensor, dist: Tensor, g_conf: Tensor, g_inter: Tensor, beta: float,
+                     need_x0: bool) -> Tuple[Tensor, Tensor]:
+    _require_cuda(xhat, x0, dist, g_conf, g_inter)
+    sfx = _suffix(xhat)
+    xhat, x0, dist = xhat.contiguous(), x0.contiguous(), dist.contiguous()
+    g_conf = g_conf.reshape(-1)[:1].float().contiguous()
+    g_inter = g_inter.reshape(-1)[:1].float().contiguous()
+    B, m, D = xhat.shape
+    gx = torch.empty_like(xhat)
+    gx0 = torch.empty_like(x0) if need_x0 else torch.empty(0, dtype=x0.dtype, device=x0.device)
+    with torch.cuda.device(xhat.device):
+        fn = getattr(_cabi.lib(), f"dddm_energy_terms_bwd_{sfx}")
+        _cabi.check(fn(_ptr(xhat), _ptr(x0), _ptr(dist), _ptr(g_conf), _ptr(g_inter), _ptr(gx),
+                       _ptr(gx0) if need_x0 else None, B, m, D, float(beta), _stream(xhat)))
+    return gx, gx0
+
+
+@energy_terms_bwd.register_fake
+def _(xhat, x0, dist, g_conf, g_inter, beta, need_x0):
+    return torch.empty_like(xhat), (torch.empty_like(x0) if need_x0 else x0.new_empty(0))
+
+
+def _energy_terms_setup(ctx, inputs, output):
+    xhat, x0, beta = inputs
+    ctx.beta = beta
+    ctx.save_for_backward(xhat, x0, output[1])
+
+
+def _energy_terms_backward(ctx, g_out, g_dist):
+    xhat, x0, dist = ctx.saved_tensors
+    need_x0 = ctx.needs_input_grad[1]
+    gx, gx0 = energy_terms_bwd(xhat, x0, dist, g_out[0:1], g_out[1:2], ctx.beta, need_x0)
+    return gx, (gx0 if need_x0 else None), None
+
+
+energy_terms_fwd.register_autograd(_energy_terms_backward, setup_context=_energy_terms_setup)
+
+
+# --------------------------------------------------------------------------------------------
+# K2: forward marginal + m-fold expansion  (dddm/schedules.py:17-25, dddm/training.py:70)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("ddm_b200::forward_marginal_expand", mutates_args=())
+def forward_marginal_expand(x0: Tensor, t: Tensor, eps: Tensor, m: int, want_xt: bool) -> Tuple[Tensor, Tensor]:
+    """x0, eps [B, ...] same shape, t [B] fp32.  Returns (xt [B, ...] or empty, xt_rep [B*m, ...] or empty if m == 0)."""
+    _require_cuda(x0, t, eps)
+    sfx = _suffix(x0)
+    if eps.shape != x0.shape or eps.dtype != x0.dtype:
+        raise ValueError("eps must match x0 in shape and dtype")
+    x0, eps = x0.contiguous(), eps.contiguous()
+    t = t.reshape(-1).float().contiguous()
+    B = x0.shape[0]
+    if t.numel() != B:
+        raise ValueError("t must have one entry per row of x0")
+    D = x0.numel() // B if B else 0
+    xt = torch.empty_like(x0) if want_xt else torch.empty(0, dtype=x0.dtype, device=x0.device)
+    rep = (torch.empty((B * m, *x0.shape[1:]), dtype=x0.dtype, device=x0.device) if m > 0 else
+           torch.empty(0, dtype=x0.dtype, device=x0.device))
+    if not want_xt and m <= 0:
+        raise ValueError("nothing to compute: want_xt is False and m == 0")
+    with torch.cuda.device(x0.device):
+        fn = getattr(_cabi.lib(), f"dddm_forward_marginal_expand_{sfx}")
+        _cabi.check(fn(_ptr(x0), _ptr(t), _ptr(eps), _ptr(xt) if want_xt else None, _ptr(rep) if m > 0 else None, B,
+                       max(m, 1), D, _stream(x0)))
+    return xt, rep
+
+
+@forward_marginal_expand.register_fake
+def _(x0, t, eps, m, want_xt):
+    B = x0.shape[0]
+    xt = torch.empty_like(x0) if want_xt else x0.new_empty(0)
+    rep = x0.new_empty((B * m, *x0.shape[1:])) if m > 0 else x0.new_empty(0)
+    return xt, rep
+
+
+def _fm_setup(ctx, inputs, output):
+    x0, t, eps, m, want_xt = inputs
+    ctx.m, ctx.want_xt = m, want_xt
+    ctx.save_for_backward(x0, t, eps)
+
+
+def _fm_backward(ctx, g_xt, g_rep):
+    # rare path (the training step never differentiates through the marginal): plain tensor algebra
+    x0, t, eps = ctx.saved_tensors
+    B = x0.shape[0]
+    g = torch.zeros_like(x0, dtype=torch.float32)
+    if ctx.want_xt and g_xt is not None:
+        g = g + g_xt.float()
+    if ctx.m > 0 and g_rep is not None:
+        g = g + g_rep.float().reshape(B, ctx.m, *x0.shape[1:]).sum(dim=1)
+    tt = t.float().reshape(B, *([1] * (x0.dim() - 1)))
+    g_x0 = ((1.0 - tt) * g).to(x0.dtype) if ctx.needs_input_grad[0] else None
+    g_eps = (tt * g).to(eps.dtype) if ctx.needs_input_grad[2] else None
+    g_t = ((eps.float() - x0.float()) * g).reshape(B, -1).sum(dim=1).to(t.dtype) if ctx.needs_input_grad[1] else None
+    return g_x0, g_t, g_eps, None, None
+
+
+forward_marginal_expand.register_autograd(_fm_backward, setup_context=_fm_setup)
+
+
+# --------------------------------------------------------------------------------------------
+# K4: logistic weight and its batch sum  (dddm/losses.py:28-35, dddm/training.py:84)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("ddm_b200::sigmoid_weight_sum", mutates_args=())
+def sigmoid_weight_sum(t: Tensor, bias: float) -> Tuple[Tensor, Tensor]:
+    """t [B] -> (w [B] fp32, sum_b w [1] fp32)."""
+    _require_cuda(t)
+    t = t.reshape(-1).float().contiguous()
+    B = t.numel()
+    w = torch.empty(B, dtype=torch.float32, device=t.device)
+    w_sum = torch.empty(1, dtype=torch.float32, device=t.device)
+    with torch.cuda.device(t.device):
+        _cabi.check(_cabi.lib().dddm_sigmoid_weight_sum_f32(_ptr(t), float(bias), _ptr(w), _ptr(w_sum), B, _stream(t)))
+    return w, w_sum
+
+
+@sigmoid_weight_sum.register_fake
+def _(t, bias):
+    return t.new_empty(t.numel(), dtype=torch.float32), t.new_empty(1, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# K3: Gaussian bridge + Algorithm-2 update  (dddm/schedules.py:28-78, dddm/sampling.py:29-31)
+# --------------------------------------------------------------------------------------------
+def _bridge_call(x_out, x, xhat0, z, s, t, eps_churn, mu_out, std_out):
+    sfx = _suffix(x)
+    N = x.shape[0]
+    D = x.numel() // N if N else 0
+    vec = int(s.numel() > 1)
+    with torch.cuda.device(x.device):
+        fn = getattr(_cabi.lib(), f"dddm_bridge_step_{sfx}")
+        _cabi.check(fn(_ptr(x_out), _ptr(x), _ptr(xhat0), _ptr(z), _ptr(s), _ptr(t), vec, float(eps_churn),
+                       _ptr(mu_out), _ptr(std_out), N, D, _stream(x)))
+
+
+def _prep_st(s: Tensor, t: Tensor, N: int, device) -> Tuple[Tensor, Tensor]:
+    s = s.reshape(-1).float().contiguous()
+    t = t.reshape(-1).float().contiguous()
+    if s.numel() != t.numel():
+        n = max(s.numel(), t.numel())
+        s, t = s.expand(n).contiguous(), t.expand(n).contiguous()
+    if s.numel() not in (1, N):
+        raise ValueError(f"s and t must be scalars or have one entry per sample ({N}), got {s.numel()}")
+    return s, t
+
+
+@torch.library.custom_op("ddm_b200::bridge_step", mutates_args=())
+def bridge_step(x: Tensor, xhat0: Tensor, z: Tensor, s: Tensor, t: Tensor, eps_churn: float) -> Tensor:
+    """x_next = mu(s, t, xhat0, x) + std(s, t) * z   (one Algorithm-2 update)."""
+    _require_cuda(x, xhat0, z, s, t)
+    if xhat0.shape != x.shape or z.shape != x.shape or xhat0.dtype != x.dtype or z.dtype != x.dtype:
+        raise ValueError("x, xhat0 and z must match in shape and dtype")
+    x, xhat0, z = x.contiguous(), xhat0.contiguous(), z.contiguous()
+    s, t = _prep_st(s, t, x.shape[0], x.device)
+    out = torch.empty_like(x)
+    _bridge_call(out, x, xhat0, z, s, t, eps_churn, None, None)
+    return out
+
+
+@bridge_step.register_fake
+def _(x, xhat0, z, s, t, eps_churn):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("ddm_b200::bridge_mu_sigma", mutates_args=())
+def bridge_mu_sigma(s: Tensor, t: Tensor, x0: Tensor, xt: Tensor, eps_churn: float) -> Tuple[Tensor, Tensor]:
+    """(mu [N, ...], std [1 or N] fp32) of gaussian_bridge_mu_sigma."""
+    _require_cuda(s, t, x0, xt)
+    if x0.shape != xt.shape or x0.dtype != xt.dtype:
+        raise ValueError("x0 and xt must match in shape and dtype")
+    x0, xt = x0.contiguous(), xt.contiguous()
+    s, t = _prep_st(s, t, xt.shape[0], xt.device)
+    mu = torch.empty_like(xt)
+    std = torch.empty(s.numel(), dtype=torch.float32, device=xt.device)
+    _bridge_call(None, xt, x0, None, s, t, eps_churn, mu, std)
+    return mu, std
+
+
+@bridge_mu_sigma.register_fake
+def _(s, t, x0, xt, eps_churn):
+    return torch.empty_like(xt), xt.new_empty(max(s.numel(), t.numel()), dtype=torch.float32)

@@ -1,0 +1,74 @@
+"""Drop-in for ``dddm/sampling.py``: Algorithm 2 with the fused bridge + update kernel (K3)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+
+@torch.no_grad()
+def sample_dddm(
+    model: torch.nn.Module,
+    n_samples: int = 4096,
+    steps: int = 20,
+    eps_churn: float = 1.0,
+    device: str = "cpu",
+    data_shape: Sequence[int] | torch.Size | None = None,
+    *,
+    noise: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+) -> torch.Tensor:
+    """Algorithm 2 on the coarse grid t_0=0 < ... < t_N=1 — reference ``dddm/sampling.py:8-32``.
+
+    Same signature, side effects (``model.to(device).eval()``) and RNG consumption order as the
+    reference (x_T, then per step xi and z), so a seeded run draws the same noise as the reference
+    on the same device.  ``noise=(x_T, xis, zs)`` (xis/zs indexed by the loop variable k) passes the
+    noise in instead.  The bridge coefficients and the update run in ONE kernel per step; the
+    times stay on the device (no per-step host synchronisation).  CUDA-only.
+    """
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("ddm_b200.sample_dddm runs on CUDA devices only (pass device='cuda'); "
+                           "there is no CPU fallback")
+    model = model.to(dev).eval()
+    B = n_samples
+    t_grid = torch.linspace(0.0, 1.0, steps + 1, device=dev)
+    if data_shape is None:
+        data_shape = (2,)
+    if noise is None:
+        x = torch.randn((B, *tuple(data_shape)), device=dev)
+    else:
+        x = noise[0].to(dev)
+    for k in reversed(range(steps)):
+        s = t_grid[k:k + 1]
+        t = t_grid[k + 1:k + 2]
+        xi = torch.randn_like(x) if noise is None else noise[1][k].to(dev)
+        xhat0 = model(x, t.repeat(B), xi)
+        z = torch.randn_like(x) if noise is None else noise[2][k].to(dev)
+        x = ops.bridge_step(x, xhat0.to(x.dtype), z, s, t, float(eps_churn))
+    return x
+
+
+def sample_dddm_sharded(model, n_samples: int, steps: int = 20, eps_churn: float = 1.0, data_shape=None, *,
+                        group=None, gather: bool = True, seed: Optional[int] = None) -> torch.Tensor:
+    """Batch-sharded Algorithm 2 across the ranks of ``group`` (BASELINE config 5).
+
+    Every rank samples ``n_samples / world`` images independently on its own GPU (no collective on
+    the data path); one ``all_gather`` at the end assembles the full batch when ``gather`` is set.
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if n_samples % world:
+        raise ValueError(f"n_samples ({n_samples}) must be divisible by the number of ranks ({world})")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if seed is not None:
+        torch.manual_seed(seed + rank)
+    local = sample_dddm(model, n_samples // world, steps, eps_churn, device=str(dev), data_shape=data_shape)
+    if world == 1 or not gather:
+        return local
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,180 @@
+/*
+ * dddm_b200.h — C ABI of the B200-native (sm_100a) DDDM hot path.
+ *
+ * The reference (edluyuan/ddm) is pure Python: it has no FFI / plugin interface, its "operator
+ * API" for this path is six Python functions.  This header is the drop-in
+ * boundary underneath them: every entry point below is what a ctypes / cffi / pybind binding of
+ * the corresponding reference function binds to, and each one cites the reference lines it
+ * replaces (paths relative to the reference root).  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - all data pointers are DEVICE pointers owned by the caller unless the name says `_host`;
+ *     nothing is allocated or freed inside (except by the explicit dddm_session_* objects);
+ *   - every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*),
+ *     re-entrant, and never throws: it returns 0 or a negative dddm_status / positive cudaError_t;
+ *   - `bf16` data is raw uint16 storage of IEEE bfloat16; accumulation is always fp32;
+ *   - scalars produced on the device stay on the device (no hidden host synchronisation).
+ */
+#ifndef DDDM_B200_H_
+#define DDDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define DDDM_ABI_VERSION 1
+
+typedef void* dddm_stream_t; /* cudaStream_t */
+typedef uint16_t dddm_bf16;  /* raw bfloat16 bits */
+
+enum dddm_status {
+    DDDM_OK = 0,
+    DDDM_ERR_NULL_POINTER = -1,
+    DDDM_ERR_BAD_SHAPE = -2,    /* B, m, D, N out of range (m must be >= 2: training.py:57-58) */
+    DDDM_ERR_BAD_ALIGNMENT = -3,
+    DDDM_ERR_UNSUPPORTED = -4,  /* shape/arch not supported by any kernel variant */
+    DDDM_ERR_BAD_ARGUMENT = -5,
+    DDDM_ERR_NO_DEVICE = -6
+};
+
+int dddm_abi_version(void);
+/* Human-readable message for a status returned by any function here (negative: dddm_status,
+ * positive: cudaError_t). Never NULL. */
+const char* dddm_strerror(int status);
+
+/* ------------------------------------------------------------------------------------------
+ * Energy-score workspace.  `workspace` passed to the energy kernels must hold
+ * dddm_energy_workspace_bytes(B, m) bytes, 16-byte aligned, and must be ZERO-INITIALISED once
+ * before first use; the kernels leave it reusable (the arrival ticket is reset by the last CTA).
+ * One workspace must not be shared by launches that may run concurrently.
+ * ------------------------------------------------------------------------------------------ */
+size_t dddm_energy_workspace_bytes(int B, int m);
+/* number of floats per row in the saved-distance buffer of the split fwd/bwd pair: m + m(m-1)/2 */
+size_t dddm_energy_dist_per_row(int m);
+
+/*
+ * K1 — fused forward + backward of the loss of distributional_training_step
+ * (dddm/training.py:77-85 with dddm/losses.py:5-25):
+ *     W     = weight_dev[0] * weight_scale          (the batch-mean logistic weight, training.py:84;
+ *                                                    weight_dev may hold an all-reduced SUM and
+ *                                                    weight_scale 1/(ranks*B): SURVEY.md §8e)
+ *     conf  = mean_{b,i}      f(|x0_b - xhat_bi|^2)
+ *     inter = mean_{b,i,j!=i} f(|xhat_bi - xhat_bj|^2),  f(d2) = (d2 + 1e-12)^(beta/2), or d2 if beta == 2.0
+ *     loss  = W * (conf - lam/(2(m-1)) * inter)
+ *     out[0..3] = {loss, conf, inter, W}           (fp32, device)
+ *     grad_xhat = d loss / d xhat                  (same dtype/layout as xhat; nullable -> forward only)
+ * xhat [B,m,D] and x0 [B,D] are contiguous row-major.
+ */
+int dddm_energy_fused_f32(const float* xhat, const float* x0, const float* weight_dev, float weight_scale,
+                          float* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
+                          float lam, dddm_stream_t stream);
+int dddm_energy_fused_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* weight_dev,
+                           float weight_scale, dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m,
+                           int D, float beta, float lam, dddm_stream_t stream);
+
+/*
+ * K1b — the API-faithful split pair behind generalized_energy_terms(x0hats, x0, beta, lam)
+ * (dddm/losses.py:5-25; `lam` is unused there and therefore absent here).
+ *   fwd: out[0..1] = {conf, inter}; dist [B, m + m(m-1)/2] fp32 receives the squared distances
+ *        (first the m confinement distances, then pairs (i<j) in row-major order) for the backward.
+ *   bwd: grad_xhat = g_conf[0]*dconf/dxhat + g_inter[0]*dinter/dxhat, and, when grad_x0 != NULL,
+ *        grad_x0 = g_conf[0]*dconf/dx0.  g_conf / g_inter are device scalars (autograd upstream grads).
+ */
+int dddm_energy_terms_fwd_f32(const float* xhat, const float* x0, float* dist, float* out, void* workspace,
+                              int B, int m, int D, float beta, dddm_stream_t stream);
+int dddm_energy_terms_fwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, float* dist, float* out,
+                               void* workspace, int B, int m, int D, float beta, dddm_stream_t stream);
+int dddm_energy_terms_bwd_f32(const float* xhat, const float* x0, const float* dist, const float* g_conf,
+                              const float* g_inter, float* grad_xhat, float* grad_x0, int B, int m, int D,
+                              float beta, dddm_stream_t stream);
+int dddm_energy_terms_bwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* dist,
+                               const float* g_conf, const float* g_inter, dddm_bf16* grad_xhat,
+                               dddm_bf16* grad_x0, int B, int m, int D, float beta, dddm_stream_t stream);
+
+/* y[i] *= scale[0] for i < n unless scale[0] == 1 (device-side test, no host sync): hands the
+ * pre-multiplied gradient of K1 to autograd when the upstream gradient is not exactly 1. */
+int dddm_scale_inplace_f32(float* y, const float* scale, size_t n, dddm_stream_t stream);
+int dddm_scale_inplace_bf16(dddm_bf16* y, const float* scale, size_t n, dddm_stream_t stream);
+
+/*
+ * K2 — forward_marginal_sample (dddm/schedules.py:17-25) fused with the m-fold expansion of
+ * dddm/training.py:70:  xt[b,:] = (1 - t[b]) * x0[b,:] + t[b] * eps[b,:];  xt_rep[b*m+i,:] = xt[b,:].
+ * xt and xt_rep are each nullable (but not both); m is ignored when xt_rep == NULL.
+ */
+int dddm_forward_marginal_expand_f32(const float* x0, const float* t, const float* eps, float* xt,
+                                     float* xt_rep, int B, int m, long D, dddm_stream_t stream);
+int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, dddm_bf16* xt,
+                                      dddm_bf16* xt_rep, int B, int m, long D, dddm_stream_t stream);
+
+/*
+ * K4 — sigmoid_weight (dddm/losses.py:28-35): w[b] = sigmoid(log((1-t)^2/(t^2+1e-12) + 1e-12) - bias);
+ * w (nullable) receives the per-row weights, w_sum (nullable) their sum over B in a fixed order
+ * (the caller all-reduces it across ranks and passes 1/(ranks*B) as weight_scale to K1).
+ */
+int dddm_sigmoid_weight_sum_f32(const float* t, float bias, float* w, float* w_sum, int B, dddm_stream_t stream);
+
+/*
+ * K3 — one Algorithm-2 update (dddm/sampling.py:29-31 with gaussian_bridge_mu_sigma,
+ * dddm/schedules.py:28-78):   x_out = c_xt*x + c_x0*xhat0 + std*z,  (c_xt, c_x0, std) from (s, t, eps_churn).
+ * s, t: device fp32, one value (st_is_vector == 0) or N values.  z nullable (-> x_out = mu).
+ * x_out may alias x.  mu_out / std_out nullable: when given they receive mu [N,D] and std [1 or N]
+ * (the return values of gaussian_bridge_mu_sigma itself).
+ */
+int dddm_bridge_step_f32(float* x_out, const float* x, const float* xhat0, const float* z, const float* s,
+                         const float* t, int st_is_vector, double eps_churn, float* mu_out, float* std_out,
+                         long N, long D, dddm_stream_t stream);
+int dddm_bridge_step_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16* xhat0, const dddm_bf16* z,
+                          const float* s, const float* t, int st_is_vector, double eps_churn, dddm_bf16* mu_out,
+                          float* std_out, long N, long D, dddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer sessions: the same fused loss called with HOST pointers (what a reference-side
+ * binding without device tensors would call; bench.py's `e2e` figure).  A session owns device
+ * buffers, pinned staging and two streams sized for (B, m, D); step_host copies the inputs in,
+ * runs K4 + K1 and copies {loss, conf, inter, W} and (optionally) grad_xhat back.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dddm_session dddm_session;
+/* dtype: 0 = fp32, 1 = bf16.  Returns NULL on failure (see dddm_last_error). */
+dddm_session* dddm_session_create(int B, int m, int D, int dtype, int device);
+void dddm_session_destroy(dddm_session*);
+/* Synchronous: returns when out_host[4] (and grad_host, if not NULL) are filled. */
+int dddm_session_step_host(dddm_session*, const void* xhat_host, const void* x0_host, const float* t_host,
+                           float w_bias, float beta, float lam, void* grad_host, float* out_host);
+/* Pipelined: enqueue step k (copy-in / compute / copy-out on rotating buffers) without waiting;
+ * dddm_session_wait drains everything enqueued so far.  Host buffers must stay valid until then
+ * and should be pinned (dddm_host_alloc) for the copies to overlap. */
+int dddm_session_enqueue_host(dddm_session*, const void* xhat_host, const void* x0_host, const float* t_host,
+                              float w_bias, float beta, float lam, void* grad_host, float* out_host);
+int dddm_session_wait(dddm_session*);
+void* dddm_host_alloc(size_t bytes); /* pinned host memory */
+void dddm_host_free(void*);
+int dddm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tuning / introspection (benchmarks and tests; never needed for correctness).
+ *   keys: "energy.cluster" (CTAs per row, 0 = auto), "energy.nv" (16-byte vectors per thread,
+ *         0 = auto), "energy.variant" (0 = auto, 1 = register-resident, 2 = shared-memory/TMA tile),
+ *         "energy.pdl" (1 = launch with programmatic dependent launch).
+ * dddm_launch_count returns the number of kernels this library has launched in this process.
+ * ------------------------------------------------------------------------------------------ */
+int dddm_set_tuning(const char* key, int value);
+int dddm_get_tuning(const char* key);
+unsigned long long dddm_launch_count(void);
+/* Describes the kernel variant the current tuning would pick for a shape, e.g.
+ * "reg<f32,M=8,VEC=4,NV=1> cluster=8 threads=96". Returns chars written (excluding NUL). */
+int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDDM_B200_H_ */

@@ -1,0 +1,292 @@
+"""GPU parity of the energy-score kernels (K1 fused, K1b split), called through the C ABI via the
+custom ops, against the CPU oracle and the golden fixtures recorded from the reference.
+
+Tolerances (BASELINE.json north_star): fp32 loss and gradients within 1e-5 relative, bf16 within
+1e-2 — relative to the largest magnitude of the reference tensor (normwise), measured against the
+fp64 oracle evaluated on the SAME (fp32- or bf16-rounded) inputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-5
+BF16_REL = 1e-2
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _names(g):
+    return [str(n) for n in g["names"]]
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    import ddm_b200  # noqa: F401  (fails loudly if the library is missing)
+    from ddm_b200 import _cabi
+
+    _cabi.lib()
+    yield cuda_device
+    for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl"):
+        _cabi.set_tuning(k, 0)
+
+
+def _fused(xhat, x0, w, beta, lam, want_grad=True):
+    from ddm_b200 import ops
+
+    wt = torch.tensor([w], dtype=torch.float32, device=xhat.device)
+    out, grad = ops.energy_fused(xhat, x0, wt, 1.0, beta, lam, want_grad)
+    return out.cpu().numpy().astype(np.float64), (grad.float().cpu().numpy() if want_grad else None)
+
+
+def _check_case(xh_np, x0_np, beta, dev, dtype=torch.float32, rel=FP32_REL, lam=1.3, w=0.7):
+    from ddm_b200 import ops
+
+    xh = torch.from_numpy(np.asarray(xh_np, dtype=np.float32)).to(dev).to(dtype)
+    x0 = torch.from_numpy(np.asarray(x0_np, dtype=np.float32)).to(dev).to(dtype)
+    # oracle on exactly the values the kernel sees
+    xh64, x064 = xh.double().cpu().numpy(), x0.double().cpu().numpy()
+    loss, conf, inter, grad = oracle.energy_loss(xh64, x064, beta, lam, w)
+    out, g = _fused(xh, x0, w, beta, lam)
+    scale = max(abs(conf), abs(inter), 1e-30)
+    assert abs(out[1] - conf) <= FP32_REL * scale, ("conf", out[1], conf)
+    assert abs(out[2] - inter) <= FP32_REL * scale, ("inter", out[2], inter)
+    assert abs(out[0] - loss) <= FP32_REL * max(abs(w) * scale, 1e-30) * 2, ("loss", out[0], loss)
+    assert abs(out[3] - w) <= 1e-7
+    gmax = np.max(np.abs(grad))
+    if gmax > 0:
+        assert _rel(g, grad) <= rel, ("grad", _rel(g, grad))
+    else:
+        assert not np.any(g)
+    # split pair: forward values, saved distances, backward with independent upstream gradients
+    o2, dist = ops.energy_terms_fwd(xh, x0, beta)
+    o2 = o2.cpu().numpy().astype(np.float64)
+    assert abs(o2[0] - conf) <= FP32_REL * scale and abs(o2[1] - inter) <= FP32_REL * scale
+    gc = torch.tensor([0.37], device=dev)
+    gi = torch.tensor([-1.9], device=dev)
+    gx, gx0 = ops.energy_terms_bwd(xh, x0, dist, gc, gi, beta, True)
+    ref_gx, ref_gx0 = oracle.energy_terms_grad(xh64, x064, beta, 0.37, -1.9, want_x0=True)
+    if np.max(np.abs(ref_gx)) > 0:
+        assert _rel(gx.float().cpu().numpy(), ref_gx) <= rel
+    if np.max(np.abs(ref_gx0)) > 0:
+        assert _rel(gx0.float().cpu().numpy(), ref_gx0) <= rel
+
+
+def test_golden_cases_fp32(dev, golden_energy):
+    g = golden_energy
+    for n in _names(g):
+        _check_case(g[f"{n}/xhat"], g[f"{n}/x0"], float(g[f"{n}/beta"]), dev)
+
+
+def test_golden_values_against_reference_outputs(dev, golden_energy):
+    """Directly against the numbers the reference produced (not via the oracle)."""
+    from ddm_b200 import ops
+
+    g = golden_energy
+    for n in _names(g):
+        xh = torch.from_numpy(g[f"{n}/xhat"]).to(dev)
+        x0 = torch.from_numpy(g[f"{n}/x0"]).to(dev)
+        beta = float(g[f"{n}/beta"])
+        out, dist = ops.energy_terms_fwd(xh, x0, beta)
+        out = out.cpu().numpy()
+        ref = np.array([g[f"{n}/conf"], g[f"{n}/inter"]])
+        assert np.max(np.abs(out - ref)) <= FP32_REL * np.max(np.abs(ref)), n
+        one, zero = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+        gx, gx0 = ops.energy_terms_bwd(xh, x0, dist, one, zero, beta, True)
+        if np.max(np.abs(g[f"{n}/g_conf"])) > 0:
+            assert _rel(gx.cpu().numpy(), g[f"{n}/g_conf"]) <= FP32_REL, n
+            assert _rel(gx0.cpu().numpy(), g[f"{n}/g_conf_x0"]) <= FP32_REL, n
+        gx, _ = ops.energy_terms_bwd(xh, x0, dist, zero, one, beta, False)
+        if np.max(np.abs(g[f"{n}/g_inter"])) > 0:
+            assert _rel(gx.cpu().numpy(), g[f"{n}/g_inter"]) <= FP32_REL, n
+
+
+def test_known_answers(dev, golden_energy):
+    g = golden_energy
+    out, grad = _fused(torch.from_numpy(g["kat1a/xhat"]).to(dev), torch.from_numpy(g["kat1a/x0"]).to(dev), 1.0, 2.0, 1.0)
+    assert out[:3].tolist() == [-1.0, 1.0, 4.0] and grad.ravel().tolist() == [-1.0, 1.0]
+    out, grad = _fused(torch.from_numpy(g["kat3/xhat"]).to(dev), torch.from_numpy(g["kat3/x0"]).to(dev), 1.0, 0.1, 1.0)
+    assert abs(out[1] - 1e-12 ** 0.05) < 1e-6 and abs(out[2] - out[1]) < 1e-7 and not grad.any()
+    assert np.isfinite(out).all()
+
+
+def test_golden_cases_bf16(dev, golden_energy):
+    g = golden_energy
+    for n in _names(g):
+        if n.startswith(("bf16grid", "early_B3_m8_D33", "late_B2_m8_D259", "early_B2_m16_D7", "dups")):
+            _check_case(g[f"{n}/xhat"], g[f"{n}/x0"], float(g[f"{n}/beta"]), dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
+def _synthetic(B, m, D, regime, seed=0):
+    """SURVEY.md §8(d) generators: CIFAR-range x0, 'early' (independent) or 'late' (x0 + 0.05 noise) draws."""
+    gen = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(B, D, generator=gen).clamp(-1, 1)
+    if regime == "early":
+        xh = torch.randn(B, m, D, generator=gen)
+    else:
+        xh = x0[:, None, :] + 0.05 * torch.randn(B, m, D, generator=gen)
+    return xh, x0
+
+
+@pytest.mark.parametrize("regime", ["early", "late"])
+@pytest.mark.parametrize("beta", [0.1, 1.0, 2.0])
+def test_headline_shape_fp32(dev, regime, beta):
+    """BASELINE config 2 at full size: B=128, m=8, D=3072."""
+    xh, x0 = _synthetic(128, 8, 3072, regime)
+    _check_case(xh.numpy(), x0.numpy(), beta, dev)
+
+
+@pytest.mark.parametrize("regime", ["early", "late"])
+def test_headline_shape_bf16(dev, regime):
+    xh, x0 = _synthetic(128, 8, 3072, regime, seed=1)
+    _check_case(xh.numpy(), x0.numpy(), 0.1, dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
+@pytest.mark.parametrize("m", [4, 8, 16, 32])
+@pytest.mark.parametrize("D", [2, 3072, 12288])
+def test_sweep_shapes(dev, m, D):
+    """BASELINE config 3 grid (m x D), beta cycling over {0.1, 1.0, 2.0}; B reduced where the oracle is slow."""
+    B = 128 if m * D <= 8 * 3072 else 16
+    for k, beta in enumerate((0.1, 1.0, 2.0)):
+        regime = "late" if (k + m) % 2 else "early"
+        xh, x0 = _synthetic(B, m, D, regime, seed=m * 7 + k)
+        _check_case(xh.numpy(), x0.numpy(), beta, dev)
+        if k == 0 and D >= 8:
+            _check_case(xh.numpy(), x0.numpy(), beta, dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
+@pytest.mark.parametrize("m,D", [(2, 1), (3, 5), (5, 130), (7, 64), (8, 259), (8, 4100), (9, 33), (12, 100), (17, 68),
+                                 (33, 40), (64, 36), (8, 96), (6, 8192)])
+def test_ragged_shapes(dev, m, D):
+    """Odd m, D not a multiple of the vector width (unaligned rows), slabs with empty trailing CTAs."""
+    for B, beta in ((1, 0.1), (3, 1.5), (5, 2.0)):
+        xh, x0 = _synthetic(B, m, D, "early", seed=B + m + D)
+        _check_case(xh.numpy(), x0.numpy(), beta, dev)
+    xh, x0 = _synthetic(2, m, D, "late", seed=99)
+    _check_case(xh.numpy(), x0.numpy(), 0.1, dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
+def test_kernel_variants_agree(dev):
+    """Every launch plan (cluster size, vectors per thread, register vs smem-tile variant) is the same function."""
+    from ddm_b200 import _cabi
+
+    xh, x0 = _synthetic(16, 8, 3072, "late", seed=5)
+    xh, x0 = xh.to(dev), x0.to(dev)
+    loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(), 0.1, 1.0, 0.5)
+    seen = set()
+    try:
+        for variant in (1, 2):
+            for cluster in (1, 2, 4, 8):
+                for nv in (1, 2):
+                    _cabi.set_tuning("energy.variant", variant)
+                    _cabi.set_tuning("energy.cluster", cluster)
+                    _cabi.set_tuning("energy.nv", nv)
+                    seen.add(_cabi.describe_energy(16, 8, 3072))
+                    out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
+                    assert abs(out[0] - loss) <= 2e-5 * abs(conf), (variant, cluster, nv)
+                    assert _rel(g, grad) <= FP32_REL, (variant, cluster, nv, _rel(g, grad))
+        for pdl in (0, 1):
+            _cabi.set_tuning("energy.variant", 0)
+            _cabi.set_tuning("energy.cluster", 0)
+            _cabi.set_tuning("energy.nv", 0)
+            _cabi.set_tuning("energy.pdl", pdl)
+            out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
+            assert _rel(g, grad) <= FP32_REL
+    finally:
+        for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl"):
+            _cabi.set_tuning(k, 0)
+    assert len(seen) >= 8, seen
+
+
+def test_deterministic_and_workspace_reuse(dev):
+    xh, x0 = _synthetic(128, 8, 3072, "early", seed=3)
+    xh, x0 = xh.to(dev), x0.to(dev)
+    first = _fused(xh, x0, 0.4, 0.1, 1.0)
+    for _ in range(5):
+        again = _fused(xh, x0, 0.4, 0.1, 1.0)
+        assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+
+
+def test_properties_full_size(dev):
+    """Size-independent properties at the headline shape (no oracle needed)."""
+    from ddm_b200 import ops
+
+    B, m, D = 128, 8, 3072
+    xh, x0 = _synthetic(B, m, D, "late", seed=11)
+    xh, x0 = xh.to(dev), x0.to(dev)
+    base, gbase = _fused(xh, x0, 1.0, 1.0, 1.0)
+    # translation invariance: distances are unchanged when every point moves by the same vector
+    shift = torch.randn(B, 1, D, device=dev) * 0.25
+    out, g = _fused(xh + shift, x0 + shift[:, 0], 1.0, 1.0, 1.0)
+    assert np.allclose(out[:3], base[:3], rtol=2e-5)
+    assert _rel(g, gbase) <= 2e-4  # inputs themselves were re-rounded by the shift
+    # permuting the draws permutes the gradient rows and leaves the scalars unchanged
+    perm = torch.randperm(m)
+    out, g = _fused(xh[:, perm].contiguous(), x0, 1.0, 1.0, 1.0)
+    assert np.allclose(out[:3], base[:3], rtol=1e-6)
+    assert _rel(g, gbase[:, perm.numpy()]) <= 1e-6
+    # homogeneity for beta = 2: f(a x) = a^2 f(x), grad(a x) = a grad(x)
+    b2, g2 = _fused(xh, x0, 1.0, 2.0, 1.0)
+    out, g = _fused(2.0 * xh, 2.0 * x0, 1.0, 2.0, 1.0)
+    assert np.allclose(out[:3], 4.0 * b2[:3], rtol=1e-6) and _rel(g, 2.0 * g2) <= 1e-6
+    # linearity in the weight, and loss == W * (conf - lam/(2(m-1)) inter)
+    out, g = _fused(xh, x0, 0.25, 1.0, 3.0)
+    assert abs(out[0] - 0.25 * (out[1] - 3.0 / (2 * (m - 1)) * out[2])) <= 1e-6 * abs(out[1])
+    # rows are independent: the batch mean is the mean of the two half-batch means
+    o1, _ = _fused(xh[:64].contiguous(), x0[:64].contiguous(), 1.0, 1.0, 1.0)
+    o2, _ = _fused(xh[64:].contiguous(), x0[64:].contiguous(), 1.0, 1.0, 1.0)
+    assert np.allclose(0.5 * (o1[1:3] + o2[1:3]), base[1:3], rtol=1e-6)
+    # sum over draws of the interaction gradient vanishes (pair terms are antisymmetric)
+    o, dist = ops.energy_terms_fwd(xh, x0, 1.0)
+    gi, _ = ops.energy_terms_bwd(xh, x0, dist, torch.zeros(1, device=dev), torch.ones(1, device=dev), 1.0, False)
+    assert float(gi.sum(dim=1).abs().max()) <= 1e-6 * float(gi.abs().max()) * m
+
+
+def test_autograd_fused_and_split(dev):
+    from ddm_b200 import generalized_energy_terms, ops
+
+    xh, x0 = _synthetic(8, 8, 256, "early", seed=21)
+    xh, x0 = xh.to(dev), x0.to(dev)
+    xh64, x064 = xh.double().cpu().numpy(), x0.double().cpu().numpy()
+    w = torch.tensor([0.6], device=dev)
+    # fused op: loss.backward() hands the kernel's gradient over; upstream scale != 1 rescales it
+    for upstream in (1.0, 2.5):
+        a = xh.clone().requires_grad_(True)
+        out, _ = ops.energy_fused(a, x0, w, 1.0, 0.1, 1.0, True)
+        (out[0] * upstream).backward()
+        _, _, _, ref = oracle.energy_loss(xh64, x064, 0.1, 1.0, 0.6)
+        assert _rel(a.grad.cpu().numpy(), upstream * ref) <= FP32_REL
+    a = xh.clone().requires_grad_(True)
+    out, _ = ops.energy_fused(a, x0, w, 1.0, 0.1, 1.0, True)
+    out[0].backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="already consumed"):
+        out[0].backward()
+    # split path: arbitrary function of (conf, inter), gradient w.r.t. both inputs
+    a = xh.clone().requires_grad_(True)
+    c = x0.clone().requires_grad_(True)
+    conf, inter = generalized_energy_terms(a, c, 1.5, 1.0)
+    (3.0 * conf - 0.5 * inter).backward()
+    ref_gx, ref_gx0 = oracle.energy_terms_grad(xh64, x064, 1.5, 3.0, -0.5, want_x0=True)
+    assert _rel(a.grad.cpu().numpy(), ref_gx) <= FP32_REL and _rel(c.grad.cpu().numpy(), ref_gx0) <= FP32_REL
+    assert conf.dim() == 0 and inter.dim() == 0 and conf.dtype == torch.float32
+    with pytest.raises(ValueError):
+        generalized_energy_terms(xh[:, :1], x0, 1.0, 1.0)
+
+
+def test_errors_are_loud(dev):
+    from ddm_b200 import generalized_energy_terms, ops
+
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        generalized_energy_terms(torch.zeros(2, 2, 2), torch.zeros(2, 2), 1.0, 1.0)
+    with pytest.raises(TypeError):
+        ops.energy_terms_fwd(torch.zeros(2, 2, 2, device=dev, dtype=torch.float64),
+                             torch.zeros(2, 2, device=dev, dtype=torch.float64), 1.0)
+    with pytest.raises(ValueError):
+        ops.energy_terms_fwd(torch.zeros(2, 2, 3, device=dev), torch.zeros(2, 2, device=dev), 1.0)

@@ -1,0 +1,262 @@
+"""GPU parity of the elementwise kernels (K2, K3, K4), the training step and the sampler."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests.helpers import MixModel
+
+pytestmark = pytest.mark.gpu
+
+
+def _names(g):
+    return [str(n) for n in g["names"]]
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    from ddm_b200 import _cabi
+
+    _cabi.lib()
+    return cuda_device
+
+
+def test_sigmoid_weight(dev, golden_weights):
+    from ddm_b200 import ops, sigmoid_weight
+
+    g = golden_weights
+    t = torch.from_numpy(g["t"]).float().to(dev)
+    for bias in (0.0, 1.0, -0.5):
+        w = sigmoid_weight(t, bias)
+        assert w.shape == t.shape and w.dtype == t.dtype
+        assert np.allclose(w.cpu().numpy(), g[f"w32_bias{bias}"], rtol=2e-6, atol=1e-12)
+        assert np.allclose(w.cpu().numpy(), g[f"w64_bias{bias}"], rtol=2e-6, atol=1e-12)
+        _, s = ops.sigmoid_weight_sum(t, bias)
+        assert abs(float(s) - g[f"w64_bias{bias}"].sum()) <= 2e-6 * g[f"w64_bias{bias}"].sum()
+    big = torch.rand(5000, device=dev)
+    w, s = ops.sigmoid_weight_sum(big, 0.3)
+    assert abs(float(s) - oracle.sigmoid_weight(big.cpu().numpy(), 0.3).sum()) <= 1e-5 * 5000
+    a = ops.sigmoid_weight_sum(big, 0.3)[1]
+    assert torch.equal(a, s)  # fixed-shape reduction: bitwise reproducible
+
+
+def test_forward_marginal_bit_exact(dev, golden_schedules):
+    from ddm_b200 import forward_marginal_sample, ops
+
+    g = golden_schedules
+    for name in ("img", "flat", "toy", "lowrank"):
+        x0, eps, t = (torch.from_numpy(g[f"fm_{name}/{k}"]).to(dev) for k in ("x0", "eps", "t"))
+        xt = forward_marginal_sample(x0, t, eps)
+        assert xt.shape == x0.shape
+        assert np.array_equal(xt.cpu().numpy(), g[f"fm_{name}/xt"]), name  # same fp32 ops as the reference's eager path
+    x0, eps, t = (torch.from_numpy(g[f"fm_img/{k}"]).to(dev) for k in ("x0", "eps", "t"))
+    xt, rep = ops.forward_marginal_expand(x0, t, eps, 5, True)
+    assert rep.shape == (4 * 5, 3, 2, 2)
+    assert torch.equal(rep.view(4, 5, 3, 2, 2), xt[:, None].expand(4, 5, 3, 2, 2))
+    # CIFAR-sized, vectorised path, fp32 and bf16, against the oracle
+    gen = torch.Generator().manual_seed(0)
+    x0 = (torch.rand(128, 3, 32, 32, generator=gen) * 2 - 1).to(dev)
+    eps = torch.randn(128, 3, 32, 32, generator=gen).to(dev)
+    t = torch.rand(128, generator=gen).to(dev)
+    _, rep = ops.forward_marginal_expand(x0, t, eps, 8, False)
+    ref, ref_rep = oracle.forward_marginal(x0, t, eps, m=8)
+    assert np.allclose(rep.cpu().numpy().reshape(1024, -1), ref_rep, rtol=0, atol=3e-7)
+    _, rep16 = ops.forward_marginal_expand(x0.bfloat16(), t, eps.bfloat16(), 8, False)
+    ref16, ref16_rep = oracle.forward_marginal(x0.bfloat16(), t, eps.bfloat16(), m=8)
+    assert np.allclose(rep16.float().cpu().numpy().reshape(1024, -1), ref16_rep, rtol=8e-3, atol=1e-3)
+
+
+def test_forward_marginal_autograd(dev):
+    from ddm_b200 import forward_marginal_sample
+
+    x0 = torch.randn(4, 6, device=dev, requires_grad=True)
+    eps = torch.randn(4, 6, device=dev, requires_grad=True)
+    t = torch.rand(4, device=dev, requires_grad=True)
+    y = forward_marginal_sample(x0, t, eps)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    tt = t.detach()[:, None]
+    assert torch.allclose(x0.grad, (1 - tt) * gy) and torch.allclose(eps.grad, tt * gy)
+    assert torch.allclose(t.grad, ((eps.detach() - x0.detach()) * gy).sum(1), atol=1e-6)
+
+
+def test_bridge_bit_exact(dev, golden_schedules):
+    from ddm_b200 import gaussian_bridge_mu_sigma, ops
+
+    g = golden_schedules
+    x0hat, xt = torch.from_numpy(g["br/x0hat"]).to(dev), torch.from_numpy(g["br/xt"]).to(dev)
+    for steps in (20, 5):
+        grid = torch.linspace(0.0, 1.0, steps + 1, device=dev)
+        for churn in (1.0, 0.0, 0.5):
+            key = f"br_grid{steps}_churn{churn}"
+            for k in range(steps):
+                mu, std = gaussian_bridge_mu_sigma(grid[k], grid[k + 1], x0hat, xt, eps_churn=churn)
+                assert std.shape == (1, 1)
+                assert np.array_equal(mu.cpu().numpy(), g[f"{key}/mu"][k]), (key, k)
+                assert float(std) == g[f"{key}/std"][k], (key, k)
+    s, t = torch.from_numpy(g["br_vec/s"]).to(dev), torch.from_numpy(g["br_vec/t"]).to(dev)
+    for churn in (1.0, 0.0, 0.7):
+        mu, std = gaussian_bridge_mu_sigma(s, t, x0hat, xt, eps_churn=churn)
+        assert std.shape == (5, 1)
+        assert np.array_equal(mu.cpu().numpy(), g[f"br_vec_churn{churn}/mu"])
+        assert np.array_equal(std.cpu().numpy(), g[f"br_vec_churn{churn}/std"])
+        z = torch.randn_like(xt)
+        nxt = ops.bridge_step(xt, x0hat, z, s, t, churn)
+        assert torch.equal(nxt, mu + std * z)
+    mu, std = gaussian_bridge_mu_sigma(s, t, torch.from_numpy(g["br_img/x0hat"]).to(dev),
+                                       torch.from_numpy(g["br_img/xt"]).to(dev), eps_churn=1.0)
+    assert std.shape == (5, 1, 1, 1) and np.array_equal(mu.cpu().numpy(), g["br_img/mu"])
+    assert np.array_equal(std.cpu().numpy(), g["br_img/std"])
+    # image-sized vectorised path against the fp64 oracle, fp32 and bf16
+    x = torch.randn(128, 3, 32, 32, device=dev)
+    h = torch.randn_like(x)
+    z = torch.randn_like(x)
+    sc, tc = torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)
+    out = ops.bridge_step(x, h, z, sc, tc, 0.8)
+    ref, _ = oracle.bridge_step(x, h, z, float(sc), float(tc), 0.8)
+    assert np.allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
+    out16 = ops.bridge_step(x.bfloat16(), h.bfloat16(), z.bfloat16(), sc, tc, 0.8)
+    ref16, _ = oracle.bridge_step(x.bfloat16(), h.bfloat16(), z.bfloat16(), float(sc), float(tc), 0.8)
+    assert np.allclose(out16.float().cpu().numpy(), ref16, rtol=8e-3, atol=2e-3)
+
+
+def test_training_step_matches_reference(dev, golden_step):
+    """The drop-in step with the recorded noise passed in reproduces the reference's loss, metrics
+    and gradients (w.r.t. the denoiser output and the model parameters)."""
+    from ddm_b200 import distributional_training_step
+
+    g = golden_step
+    for n in _names(g):
+        m, beta, lam, w_bias = g[f"{n}/hyper"]
+        m = int(m)
+        model = MixModel().to(dev)
+        x0, t, eps, xi = (torch.from_numpy(g[f"{n}/{k}"]).to(dev) for k in ("x0", "t", "eps", "xi"))
+        seen = {}
+
+        def hook(_mod, args, out):
+            seen["xt_rep"], seen["t_rep"], seen["xi"] = (a.detach() for a in args)
+            out.retain_grad()
+            seen["out"] = out
+
+        h = model.register_forward_hook(hook)
+        loss, metrics = distributional_training_step(model, x0, m=m, beta=float(beta), lam=float(lam),
+                                                     w_bias=float(w_bias), t=t, eps=eps, xi=xi)
+        h.remove()
+        loss.backward()
+        assert loss.dim() == 0 and loss.dtype == x0.dtype
+        assert list(metrics) == ["loss", "confidence", "interaction", "weight"]
+        assert all(isinstance(v, float) for v in metrics.values())
+        got = np.array([metrics[k] for k in ("loss", "confidence", "interaction", "weight")])
+        assert np.allclose(got, g[f"{n}/scalars"], rtol=1e-5, atol=1e-7), (n, got, g[f"{n}/scalars"])
+        B = x0.shape[0]
+        assert np.array_equal(seen["xt_rep"].view(B, m, *x0.shape[1:])[:, 0].cpu().numpy(), g[f"{n}/xt"])
+        assert np.allclose(seen["out"].detach().cpu().numpy().reshape(g[f"{n}/xhat"].shape), g[f"{n}/xhat"],
+                           rtol=1e-5, atol=1e-6)
+        gref = g[f"{n}/grad_xhat"]
+        gx = seen["out"].grad.cpu().numpy().reshape(gref.shape)
+        assert np.max(np.abs(gx - gref)) <= 2e-5 * np.max(np.abs(gref)), n
+        pg = np.array([float(model.a.grad), float(model.b.grad), float(model.c.grad)])
+        assert np.allclose(pg, g[f"{n}/param_grads"], rtol=2e-4, atol=1e-7), (n, pg, g[f"{n}/param_grads"])
+    with pytest.raises(ValueError, match="m must be >= 2"):
+        distributional_training_step(MixModel().to(dev), torch.zeros(2, 2, device=dev), m=1, beta=1.0, lam=1.0,
+                                     w_bias=0.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        distributional_training_step(MixModel(), torch.zeros(2, 2), m=2, beta=1.0, lam=1.0, w_bias=0.0)
+
+
+def test_training_step_rng_order_and_deferred_metrics(dev):
+    """Seeded run draws rand(B), randn_like(x0), randn(B,m,...) in the reference's order (training.py:65-69)."""
+    from ddm_b200 import DeferredMetrics, distributional_training_step
+
+    model = MixModel().to(dev)
+    x0 = torch.randn(8, 3, 4, 4, device=dev).clamp(-1, 1)
+    torch.manual_seed(7)
+    loss_a, met = distributional_training_step(model, x0, m=4, beta=0.1, lam=1.0, w_bias=0.0, sync_metrics=False)
+    assert isinstance(met, DeferredMetrics) and met.tensor.is_cuda
+    torch.manual_seed(7)
+    t = torch.rand(8, device=dev)
+    eps = torch.randn_like(x0)
+    xi = torch.randn((8, 4, 3, 4, 4), device=dev)
+    loss_b, met_b = distributional_training_step(model, x0, m=4, beta=0.1, lam=1.0, w_bias=0.0, t=t, eps=eps, xi=xi)
+    assert torch.equal(loss_a, loss_b)
+    assert met["loss"] == met_b["loss"] and dict(met) == met_b
+    # x0.requires_grad routes through the split kernels and still matches
+    x0g = x0.clone().requires_grad_(True)
+    loss_c, _ = distributional_training_step(model, x0g, m=4, beta=0.1, lam=1.0, w_bias=0.0, t=t, eps=eps, xi=xi)
+    loss_c.backward()
+    assert abs(float(loss_c) - float(loss_b)) <= 1e-5 * abs(float(loss_b)) and x0g.grad is not None
+
+
+def test_sampler_matches_reference(dev, golden_sampler):
+    from ddm_b200 import sample_dddm
+
+    g = golden_sampler
+    for n in _names(g):
+        steps, churn = g[f"{n}/hyper"]
+        model = MixModel().train()
+        noise = tuple(torch.from_numpy(g[f"{n}/{k}"]) for k in ("x_init", "xis", "zs"))
+        x = sample_dddm(model, n_samples=noise[0].shape[0], steps=int(steps), eps_churn=float(churn), device=str(dev),
+                        data_shape=noise[0].shape[1:], noise=noise)
+        assert not model.training and next(model.parameters()).is_cuda
+        assert x.shape == g[f"{n}/x_final"].shape
+        # the bridge is bit-exact; MixModel's tanh differs by ulps between CPU and GPU libm
+        assert np.allclose(x.cpu().numpy(), g[f"{n}/x_final"], rtol=2e-5, atol=2e-5), n
+    torch.manual_seed(3)
+    a = sample_dddm(MixModel(), n_samples=16, steps=3, device=str(dev))
+    torch.manual_seed(3)
+    x = torch.randn(16, 2, device=dev)
+    assert a.shape == (16, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sample_dddm(MixModel(), n_samples=2, steps=1, device="cpu")
+
+
+def test_host_session_matches_device_path(dev):
+    """C-ABI with HOST buffers (bench.py's e2e path) == device path == oracle."""
+    from ddm_b200 import _cabi
+
+    L = _cabi.lib()
+    B, m, D = 32, 8, 768
+    gen = torch.Generator().manual_seed(2)
+    x0 = torch.randn(B, D, generator=gen).clamp(-1, 1)
+    xh = x0[:, None] + 0.05 * torch.randn(B, m, D, generator=gen)
+    t = torch.rand(B, generator=gen)
+    w = oracle.sigmoid_weight(t.numpy(), 0.2).mean()
+    loss, conf, inter, grad = oracle.energy_loss(xh.numpy(), x0.numpy(), 0.1, 1.0, w)
+    for dtype, code, rel in ((torch.float32, 0, 1e-5), (torch.bfloat16, 1, 1e-2)):
+        a, c = xh.to(dtype).contiguous().pin_memory(), x0.to(dtype).contiguous().pin_memory()
+        if dtype == torch.bfloat16:
+            loss, conf, inter, grad = oracle.energy_loss(a, c, 0.1, 1.0, w)
+        gout = torch.empty_like(a).pin_memory()
+        out = torch.empty(4, dtype=torch.float32).pin_memory()
+        s = L.dddm_session_create(B, m, D, code, dev.index or 0)
+        assert s
+        try:
+            for _ in range(4):  # more steps than slots: exercises buffer rotation
+                _cabi.check(L.dddm_session_step_host(s, a.data_ptr(), c.data_ptr(), t.data_ptr(), 0.2, 0.1, 1.0,
+                                                     gout.data_ptr(), out.data_ptr()))
+            got = out.numpy().astype(np.float64)
+            assert np.allclose(got, [loss, conf, inter, w], rtol=2e-5, atol=1e-7)
+            assert np.max(np.abs(gout.float().numpy() - grad)) <= rel * np.max(np.abs(grad))
+            outs = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(7)]
+            for o in outs:
+                _cabi.check(L.dddm_session_enqueue_host(s, a.data_ptr(), c.data_ptr(), t.data_ptr(), 0.2, 0.1, 1.0,
+                                                        None, o.data_ptr()))
+            _cabi.check(L.dddm_session_wait(s))
+            assert all(torch.equal(o, out) for o in outs)
+        finally:
+            L.dddm_session_destroy(s)
+    assert not L.dddm_session_create(0, 8, 4, 0, 0) and L.dddm_last_error() == -2
+    p = L.dddm_host_alloc(1024)
+    assert p
+    ctypes.memset(p, 0, 1024)
+    L.dddm_host_free(p)
+
+
+def test_launch_counter(dev):
+    from ddm_b200 import _cabi, ops
+
+    before = _cabi.launch_count()
+    ops.sigmoid_weight_sum(torch.rand(16, device=dev), 0.0)
+    assert _cabi.launch_count() == before + 1
