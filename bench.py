@@ -150,7 +150,9 @@ def main() -> None:
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget (rank 0, N=1 only)")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
-    ap.add_argument("--sets", type=int, default=0, help="rotating input sets (0 = enough to exceed 2x L2)")
+    ap.add_argument("--sets", type=int, default=0, help="rotating input sets (0 = enough to exceed 8x L2)")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="streams the independent steps are issued on round-robin inside the CUDA graph (1 = serialized)")
     ap.add_argument("--tune", default="", help="comma list key=value for dddm_set_tuning, e.g. energy.cluster=4")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -179,7 +181,7 @@ def main() -> None:
     tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     esz = 4 if args.dtype == "f32" else 2
     algo_bytes = (2 * B * M * D + B * D) * esz  # read xhat + x0, write grad
-    nsets = args.sets or max(4, -(-2 * L2_BYTES // algo_bytes) + 1)  # working set > 2x L2: every launch is HBM-cold
+    nsets = args.sets or max(4, -(-8 * L2_BYTES // algo_bytes))  # working set > 8x L2: every launch reads HBM-cold data
     fn = getattr(L, f"dddm_energy_fused_{args.dtype}")
     K, W = max(1, args.steps), max(3, args.warmup)
 
@@ -204,38 +206,52 @@ def main() -> None:
         _cabi.check(fn(s["xh"].data_ptr(), s["x0"].data_ptr(), s["wsum"].data_ptr(), wscale, s["grad"].data_ptr(),
                        s["out"].data_ptr(), s["ws"].data_ptr(), B, M, D, BETA, LAM, cuda_stream))
 
-    def capture(n):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=stream):
-            for i in range(n):
-                launch(sets[i % nsets], torch.cuda.current_stream().cuda_stream)
-        return g
+    def make_runner(nstreams):
+        """Returns run_steps(n): n fused launches over the rotating sets.  With nstreams > 1 the steps
+        (independent minibatches) are issued round-robin on several streams forked/joined inside the graph."""
+        sides = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
 
-    use_graph = not args.no_graph
-    if use_graph:
-        chunk = nsets * max(1, 240 // nsets)
-        g_full = capture(chunk)
-        g_rem = capture(K % chunk) if K % chunk else None
+        def capture(n):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                main = torch.cuda.current_stream()
+                for sd in sides:
+                    sd.wait_stream(main)
+                for i in range(n):
+                    st = main if i % nstreams == 0 else sides[i % nstreams - 1]
+                    launch(sets[i % nsets], st.cuda_stream)
+                for sd in sides:
+                    main.wait_stream(sd)
+            return g
 
-        def run_steps(n):
+        if args.no_graph:
+            def run_plain(n):
+                for i in range(n):
+                    launch(sets[i % nsets], stream.cuda_stream)
+            return run_plain
+        chunk = nsets * max(1, 480 // nsets)
+        graphs = {chunk: capture(chunk)}
+
+        def run_graph(n):
             full, rem = divmod(n, chunk)
             for _ in range(full):
-                g_full.replay()
+                graphs[chunk].replay()
             if rem:
-                if n == K and g_rem is not None:
-                    g_rem.replay()
-                else:
-                    for i in range(rem):
-                        launch(sets[i % nsets], stream.cuda_stream)
-    else:
-        def run_steps(n):
-            for i in range(n):
-                launch(sets[i % nsets], stream.cuda_stream)
+                if rem not in graphs:
+                    graphs[rem] = capture(rem)
+                graphs[rem].replay()
+        return run_graph
+
+    use_graph = not args.no_graph
+    nstreams = max(1, args.streams) if use_graph else 1
+    run_steps = make_runner(nstreams)
+    run_serial = make_runner(1) if nstreams > 1 else run_steps
 
     launches_before = _cabi.launch_count()
     with torch.cuda.stream(stream):
         run_steps(W)
-        run_steps(K)  # extra untimed pass of the whole region: clocks and caches in steady state
+        run_steps(K)  # extra untimed pass of the whole region: clocks and caches in steady state (also captures graphs)
+        run_serial(min(K, 2000))
         stream.synchronize()
         if world > 1:
             dist.barrier()
@@ -253,6 +269,14 @@ def main() -> None:
             e1.record(stream)
             e1.synchronize()
             times.append(e0.elapsed_time(e1) * 1e-3)
+        # the same steps strictly serialized on ONE stream (reported for transparency, not the headline)
+        ks = min(K, 2000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run_serial(ks)
+        e1.record(stream)
+        e1.synchronize()
+        serial_ms = e0.elapsed_time(e1) / ks
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -321,9 +345,13 @@ def main() -> None:
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.dtype), "rows_per_gpu": B, "global_rows": B * world,
                        "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
-                       "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 2x L2 "
+                       "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 8x L2 "
                                     f"(every launch reads HBM-cold inputs)",
-                       "launch": "CUDA graphs of back-to-back launches, one stream" if use_graph else "python launches",
+                       "launch": (f"CUDA graphs; the independent steps are issued round-robin on {nstreams} streams "
+                                  f"(fork/join inside the graph) so consecutive minibatches overlap" if use_graph
+                                  else "python launches, one stream"),
+                       "single_stream_ms_per_step": serial_ms,
+                       "single_stream_rows_per_s": B / (serial_ms * 1e-3),
                        "timed_region": f"median of {len(times)} repetitions of exactly {K} steps (CUDA events on the "
                                        f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
                        "tuning": args.tune or "auto"},

@@ -1,0 +1,137 @@
+"""PyTorch denoiser backbones x0hat = f(x_t, t, xi) used by the benchmarks and the launcher.
+
+The backbones are OUT of the hot-path scope (BASELINE.json: "the MLP/DiT backbones stay in
+PyTorch"); they exist here only because ``/root/reference`` is not present on the GPU box and the
+DiT / sampler throughput configs need a model of the reference's architecture with random
+weights.  Same architecture, parameter names and shapes as the reference's ``dddm/model.py``
+(``DDDMMLP`` :41-67, ``DDDMDiT`` :183-244 — default DiT = 14,523,312 parameters), so a reference
+checkpoint's ``state_dict`` loads; the attention uses ``scaled_dot_product_attention`` instead of
+the reference's explicit softmax(qk^T)v (same math).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class _FourierTime(nn.Module):
+    """sin/cos of 2*pi*k*t for k = 1..n (reference ``TimeFeat``); ``freq`` is a frozen parameter."""
+
+    def __init__(self, n: int):
+        super().__init__()
+        self.freq = nn.Parameter(torch.arange(1, n + 1, dtype=torch.float32), requires_grad=False)
+
+    def forward(self, t: torch.Tensor) -> torch.Tensor:
+        ang = (2.0 * math.pi) * t[:, None] * self.freq[None, :]
+        return torch.cat((ang.sin(), ang.cos()), dim=-1)
+
+
+class DDDMMLP(nn.Module):
+    """Toy 2-D denoiser: [x_t (2), xi (2), time features] -> x0hat (2); 4 hidden SiLU layers."""
+
+    def __init__(self, time_dim: int = 32, hidden: int = 128):
+        super().__init__()
+        self.tfeat = _FourierTime(time_dim // 2)
+        widths = [4 + time_dim] + [hidden] * 4
+        layers: list[nn.Module] = []
+        for a, b in zip(widths[:-1], widths[1:]):
+            layers += [nn.Linear(a, b), nn.SiLU()]
+        layers.append(nn.Linear(hidden, 2))
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, xt, t, xi):
+        return self.net(torch.cat((xt, xi, self.tfeat(t)), dim=-1))
+
+
+def _sinusoidal(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    half = dim // 2
+    k = torch.arange(half, device=t.device, dtype=t.dtype)
+    freqs = torch.exp(k * (-math.log(max_period) / max(half - 1, 1)))
+    ang = t.reshape(-1, 1) * freqs
+    emb = torch.cat((ang.sin(), ang.cos()), dim=-1)
+    return F.pad(emb, (0, 1)) if dim % 2 else emb
+
+
+class _Proj(nn.Module):
+    """Holder so parameter names read ``<name>.proj.*`` like the reference's PatchEmbed / PatchUnembed."""
+
+    def __init__(self, proj: nn.Module):
+        super().__init__()
+        self.proj = proj
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int, heads: int):
+        super().__init__()
+        if dim % heads:
+            raise ValueError("dim must be divisible by num_heads")
+        self.heads = heads
+        self.qkv = nn.Linear(dim, 3 * dim)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        b, n, c = x.shape
+        q, k, v = self.qkv(x).view(b, n, 3, self.heads, c // self.heads).permute(2, 0, 3, 1, 4)
+        y = F.scaled_dot_product_attention(q, k, v)
+        return self.proj(y.transpose(1, 2).reshape(b, n, c))
+
+
+class _MLP(nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim: int, heads: int, mlp_ratio: float):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ff = _MLP(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.ff(self.norm2(x))
+
+
+class DDDMDiT(nn.Module):
+    """DiT-S/4-style image denoiser: cat(x_t, xi) -> 4x4 patches -> ``depth`` pre-norm blocks -> unpatchify."""
+
+    def __init__(self, img_size: int = 32, patch_size: int = 4, in_channels: int = 6, out_channels: int = 3,
+                 embed_dim: int = 384, depth: int = 8, num_heads: int = 6, time_embed_dim: int = 256,
+                 mlp_ratio: float = 4.0):
+        super().__init__()
+        if img_size % patch_size:
+            raise ValueError("Image size must be divisible by patch size")
+        self.img_size, self.patch_size, self.out_channels = img_size, patch_size, out_channels
+        self.embed_dim, self.time_embed_dim = embed_dim, time_embed_dim
+        self.grid = img_size // patch_size
+        self.patch_embed = _Proj(nn.Conv2d(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.grid * self.grid, embed_dim))
+        self.time_mlp = nn.Sequential(nn.Linear(time_embed_dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, embed_dim))
+        self.blocks = nn.ModuleList(_Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth))
+        self.norm = nn.LayerNorm(embed_dim)
+        self.unembed = _Proj(nn.Linear(embed_dim, out_channels * patch_size * patch_size))
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+
+    def forward(self, xt, t, xi):
+        if xt.shape != xi.shape:
+            raise ValueError("xt and xi must have the same shape")
+        if xt.dim() != 4:
+            raise ValueError("Expecting image tensors with shape [B, C, H, W]")
+        tokens = self.patch_embed.proj(torch.cat((xt, xi), dim=1)).flatten(2).transpose(1, 2)
+        temb = self.time_mlp(_sinusoidal(t.reshape(-1).to(tokens.dtype), self.time_embed_dim))
+        h = tokens + temb[:, None, :] + self.pos_embed
+        for blk in self.blocks:
+            h = blk(h)
+        y = self.unembed.proj(self.norm(h))
+        g, p, c = self.grid, self.patch_size, self.out_channels
+        y = y.view(-1, g, g, c, p, p).permute(0, 3, 1, 4, 2, 5)
+        return y.reshape(-1, c, self.img_size, self.img_size)

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "energy.cuh"
+#include "energy_smem_plan.h"
 
 namespace dddm {
 
@@ -72,8 +73,15 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     p.row_partials = reinterpret_cast<float*>(ws + 1);
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
+    // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel
+    // (m <= 8, any alignment) > chunked smem-tile kernel (any m <= 64)
     const int variant = tuning().variant;
-    if (variant != 2) {
+    if (variant == 0 || variant == 3) {
+        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al);
+        if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
+        if (variant == 3) return DDDM_ERR_UNSUPPORTED;
+    }
+    if (variant == 0 || variant == 1) {
         RegPlan plan = plan_reg(p.m, p.D, (int)sizeof(T), al, false);
         if (plan.ok) return launch_energy_reg<T>(p, plan, stream);
         if (variant == 1) return DDDM_ERR_UNSUPPORTED;
@@ -225,6 +233,7 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.nv")) t.nv = value;
     else if (!strcmp(key, "energy.variant")) t.variant = value;
     else if (!strcmp(key, "energy.pdl")) t.pdl = value;
+    else if (!strcmp(key, "energy.threads")) t.threads = value;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -235,6 +244,7 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.nv")) return t.nv;
     if (!strcmp(key, "energy.variant")) return t.variant;
     if (!strcmp(key, "energy.pdl")) return t.pdl;
+    if (!strcmp(key, "energy.threads")) return t.threads;
     return DDDM_ERR_BAD_ARGUMENT;
 }
 unsigned long long dddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -245,7 +255,15 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     const int es = dtype == 1 ? 2 : 4;
     const bool al = ((long)D * es) % 16 == 0;
     int n;
-    if (tuning().variant != 2) {
+    const int variant = tuning().variant;
+    if (variant == 0 || variant == 3) {
+        SmemPlan sp = plan_smem(m, D, es, al);
+        if (sp.ok)
+            return snprintf(buf, buflen, "smem<%s,M=%d> tma-bulk f32x2 cluster=%d threads=%d slab_vecs=%d smem=%zu",
+                            dtype == 1 ? "bf16" : "f32", m, sp.cluster, sp.threads, sp.slab_vecs, sp.smem_bytes);
+        if (variant == 3) return snprintf(buf, buflen, "unsupported");
+    }
+    if (variant == 0 || variant == 1) {
         RegPlan r = plan_reg(m, D, es, al, false);
         if (r.ok) {
             n = snprintf(buf, buflen, "reg<%s,M=%d,VEC=%d,NV=%d> cluster=%d threads=%d", dtype == 1 ? "bf16" : "f32", m,

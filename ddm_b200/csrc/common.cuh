@@ -18,7 +18,8 @@ void count_launch();
 struct Tuning {
     int cluster = 0;  // CTAs per row (0 = auto)
     int nv = 0;       // 16-byte vectors per thread (0 = auto)
-    int variant = 0;  // 0 auto, 1 register-resident, 2 smem/TMA tile
+    int variant = 0;  // 0 auto, 1 register-resident, 2 generic smem/TMA tile, 3 TMA-staged packed-fp32 (m <= 8)
+    int threads = 0;  // threads per CTA for variant 3 (0 = auto)
     int pdl = 0;      // programmatic dependent launch
 };
 Tuning& tuning();

@@ -51,6 +51,36 @@ int launch_energy_reg(const EnergyParams& p, const RegPlan& plan, cudaStream_t s
 template <typename T>
 int launch_energy_bwd_reg(const EnergyParams& p, const RegPlan& plan, cudaStream_t stream);
 
+// Launch with optional cluster dimension and programmatic dependent launch (PDL).
+template <typename K, typename... Args>
+inline int launch_with_attrs(K kernel, dim3 grid, dim3 block, size_t smem, int cluster, cudaStream_t stream,
+                             Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    int n = 0;
+    if (cluster > 1) {
+        attrs[n].id = cudaLaunchAttributeClusterDimension;
+        attrs[n].val.clusterDim.x = cluster;
+        attrs[n].val.clusterDim.y = 1;
+        attrs[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (tuning().pdl) {
+        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = n;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    count_launch();
+    return (int)e;
+}
+
 // Shared-memory tile kernels for any m (energy_tile.cu).
 struct TilePlan {
     bool ok;
@@ -66,6 +96,16 @@ template <typename T>
 int launch_energy_tile(const EnergyParams& p, const TilePlan& plan, cudaStream_t stream);
 template <typename T>
 int launch_energy_bwd_tile(const EnergyParams& p, const TilePlan& plan, cudaStream_t stream);
+
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // ---- deterministic cross-row reduction, executed by the last arriving row ------------------
 // Called by ONE warp of the CTA that owns row b after its per-row sums are known.

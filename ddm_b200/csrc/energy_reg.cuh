@@ -22,15 +22,6 @@ namespace cg = cooperative_groups;
 constexpr int kRegMaxThreads = 256;
 constexpr int kRegMaxCluster = 8;
 
-__device__ __forceinline__ void cluster_arrive_relaxed() {
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_arrive_release() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void cluster_wait_acquire() {
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // Load the NV vectors of all M draws and of x0 owned by this thread.  Slots past the slab end
 // are zero-filled so that they contribute nothing to any distance.
@@ -151,33 +142,32 @@ energy_fused_reg_kernel(const EnergyParams p, const int vec_per_cta, const int c
     WR::run(acc, s_warp[warp], lane);
     __syncthreads();
 
-    float total = 0.f;
-    if (tid < P) {
-        for (int w = 0; w < nwarps; ++w) total += s_warp[w][tid];
-    }
+    // blockDim may be smaller than P (32 threads, 36 slots): every per-slot step strides over the slots
     if (cluster_size > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster_wait_acquire();  // phase 0 complete: every CTA of the cluster is running
-        if (tid < P) {
-            for (int r = 0; r < cluster_size; ++r) {
-                float* peer = cluster.map_shared_rank(&s_cluster[0][0], r);
-                peer[rank * P + tid] = total;  // push my partial into every peer's table
-            }
+        for (int q = tid; q < P; q += blockDim.x) {
+            float t = 0.f;
+            for (int w = 0; w < nwarps; ++w) t += s_warp[w][q];
+            for (int r = 0; r < cluster_size; ++r)  // push my partial into every peer's table
+                cluster.map_shared_rank(&s_cluster[0][0], r)[rank * P + q] = t;
         }
         cluster_arrive_release();
         cluster_wait_acquire();
-        if (tid < P) {
-            total = 0.f;
-            for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][tid];  // fixed order: deterministic
-        }
     }
-    if (tid < P) {
-        s_val[tid] = pow_value(total, p.pw);
+    for (int q = tid; q < P; q += blockDim.x) {
+        float total = 0.f;
+        if (cluster_size > 1) {
+            for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][q];  // fixed order: deterministic
+        } else {
+            for (int w = 0; w < nwarps; ++w) total += s_warp[w][q];
+        }
+        s_val[q] = pow_value(total, p.pw);
         if (p.grad_xhat != nullptr) {
             const float cl = p.lam / (2.0f * (float)(M - 1));
-            s_coef[tid] = (tid < M) ? conf_coef(total, W, p) : pair_coef(total, -W * cl, p);
+            s_coef[q] = (q < M) ? conf_coef(total, W, p) : pair_coef(total, -W * cl, p);
         }
-        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + tid] = total;
+        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + q] = total;
     }
     __syncthreads();
 
@@ -214,9 +204,9 @@ energy_bwd_reg_kernel(const EnergyParams p) {
     float x[NV][M + 1][VEC];
     bool ok[NV];
     load_tile_regs<T, M, VEC, NV>(xrow, crow, p.D, v_begin + tid, nvec, blockDim.x, x, ok);
-    if (tid < P) {
-        const float d2 = p.dist[(long)b * P + tid];
-        s_coef[tid] = (tid < M) ? conf_coef(d2, p.g_conf[0], p) : pair_coef(d2, p.g_inter[0], p);
+    for (int q = tid; q < P; q += blockDim.x) {
+        const float d2 = p.dist[(long)b * P + q];
+        s_coef[q] = (q < M) ? conf_coef(d2, p.g_conf[0], p) : pair_coef(d2, p.g_inter[0], p);
     }
     cudaTriggerProgrammaticLaunchCompletion();
     __syncthreads();
@@ -230,34 +220,6 @@ energy_bwd_reg_kernel(const EnergyParams p) {
 }
 
 // ---- host-side dispatch ------------------------------------------------------------------
-template <typename K, typename... Args>
-inline int launch_with_attrs(K kernel, dim3 grid, dim3 block, int cluster, cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attrs[2];
-    int n = 0;
-    if (cluster > 1) {
-        attrs[n].id = cudaLaunchAttributeClusterDimension;
-        attrs[n].val.clusterDim.x = cluster;
-        attrs[n].val.clusterDim.y = 1;
-        attrs[n].val.clusterDim.z = 1;
-        ++n;
-    }
-    if (tuning().pdl) {
-        attrs[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attrs[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
-    cfg.attrs = attrs;
-    cfg.numAttrs = n;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
-    count_launch();
-    return (int)e;
-}
-
 template <typename T, int M>
 int launch_energy_reg_m(const EnergyParams& p, const RegPlan& plan, cudaStream_t stream) {
     constexpr int V = Elem<T>::kVec;
@@ -265,13 +227,13 @@ int launch_energy_reg_m(const EnergyParams& p, const RegPlan& plan, cudaStream_t
     const int vec_per_cta = (int)((nvec + plan.cluster - 1) / plan.cluster);
     dim3 grid(plan.cluster, p.B), block(plan.threads);
     if (plan.vec == 1)
-        return launch_with_attrs(energy_fused_reg_kernel<T, M, 1, 1>, grid, block, plan.cluster, stream, p, vec_per_cta,
+        return launch_with_attrs(energy_fused_reg_kernel<T, M, 1, 1>, grid, block, 0, plan.cluster, stream, p, vec_per_cta,
                                  plan.cluster);
     if (plan.nv == 1)
-        return launch_with_attrs(energy_fused_reg_kernel<T, M, V, 1>, grid, block, plan.cluster, stream, p, vec_per_cta,
+        return launch_with_attrs(energy_fused_reg_kernel<T, M, V, 1>, grid, block, 0, plan.cluster, stream, p, vec_per_cta,
                                  plan.cluster);
     if constexpr (sizeof(T) == 4) {  // two vectors per thread only pay off (and fit) for fp32
-        return launch_with_attrs(energy_fused_reg_kernel<T, M, V, 2>, grid, block, plan.cluster, stream, p,
+        return launch_with_attrs(energy_fused_reg_kernel<T, M, V, 2>, grid, block, 0, plan.cluster, stream, p,
                                  vec_per_cta, plan.cluster);
     }
     return DDDM_ERR_UNSUPPORTED;
@@ -283,10 +245,10 @@ int launch_energy_bwd_reg_m(const EnergyParams& p, const RegPlan& plan, cudaStre
     const long nvec = p.D / plan.vec;
     const long per_cta = (long)plan.threads * plan.nv;
     dim3 grid((unsigned)((nvec + per_cta - 1) / per_cta), p.B), block(plan.threads);
-    if (plan.vec == 1) return launch_with_attrs(energy_bwd_reg_kernel<T, M, 1, 1>, grid, block, 1, stream, p);
-    if (plan.nv == 1) return launch_with_attrs(energy_bwd_reg_kernel<T, M, V, 1>, grid, block, 1, stream, p);
+    if (plan.vec == 1) return launch_with_attrs(energy_bwd_reg_kernel<T, M, 1, 1>, grid, block, 0, 1, stream, p);
+    if (plan.nv == 1) return launch_with_attrs(energy_bwd_reg_kernel<T, M, V, 1>, grid, block, 0, 1, stream, p);
     if constexpr (sizeof(T) == 4) {
-        return launch_with_attrs(energy_bwd_reg_kernel<T, M, V, 2>, grid, block, 1, stream, p);
+        return launch_with_attrs(energy_bwd_reg_kernel<T, M, V, 2>, grid, block, 0, 1, stream, p);
     }
     return DDDM_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,41 @@
+// fp32 instantiations of the TMA-staged packed-fp32 energy kernel + its shape planner.
+#include "energy_smem_launch.cuh"
+
+namespace dddm {
+
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16) {
+    SmemPlan s{};
+    s.ok = false;
+    const int vecw = 16 / elem_size;
+    if (m < 2 || m > 8 || D < 1 || !aligned16 || D % vecw != 0) return s;
+    const long nvec = D / vecw;
+    const Tuning& t = tuning();
+    int cluster = t.cluster;
+    if (!(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8)) {
+        // auto: whole rows per CTA whenever the (m+1) x D tile leaves room for two CTAs per SM
+        // (measured on B200: fewer, fatter CTAs beat D-split clusters — no DSMEM round trip)
+        cluster = 1;
+        while (cluster < 8 && (size_t)(m + 1) * ((nvec + cluster - 1) / cluster) * 16 > 112 * 1024) cluster *= 2;
+    }
+    const long slab = (nvec + cluster - 1) / cluster;
+    const size_t smem = (size_t)(m + 1) * slab * 16;
+    if (smem > 200 * 1024) return s;  // slab too wide: the chunked tile kernel handles it
+    int threads = t.threads;
+    if (threads < 32 || threads > kSmemMaxThreads || threads % 32) {
+        threads = (int)((slab + 31) / 32 * 32);  // auto: 128 compute threads, fewer for narrow slabs
+        if (threads > 128) threads = 128;
+        if (threads < 32) threads = 32;
+    }
+    s.cluster = cluster;
+    s.threads = threads;
+    s.slab_vecs = (int)slab;
+    s.smem_bytes = smem;
+    s.ok = true;
+    return s;
+}
+
+template <>
+int launch_energy_smem<float>(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
+    DDDM_DISPATCH_M_SMEM(float, p, plan, stream)
+}
+}  // namespace dddm

@@ -1,0 +1,16 @@
+// energy_smem_plan.h — host-visible plan of the TMA-staged packed-fp32 kernel (no device code).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "energy.cuh"
+
+namespace dddm {
+struct SmemPlan {
+    bool ok;
+    int cluster, threads, slab_vecs;
+    size_t smem_bytes;
+};
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16);
+template <typename T>
+int launch_energy_smem(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
+}  // namespace dddm

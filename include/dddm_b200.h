@@ -159,9 +159,10 @@ int dddm_last_error(void);
 
 /* ------------------------------------------------------------------------------------------
  * Tuning / introspection (benchmarks and tests; never needed for correctness).
- *   keys: "energy.cluster" (CTAs per row, 0 = auto), "energy.nv" (16-byte vectors per thread,
- *         0 = auto), "energy.variant" (0 = auto, 1 = register-resident, 2 = shared-memory/TMA tile),
- *         "energy.pdl" (1 = launch with programmatic dependent launch).
+ *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
+ *         3 = TMA-staged packed-fp32 kernel for m <= 8), "energy.cluster" (CTAs per row, 0 = auto),
+ *         "energy.threads" (threads per CTA of variant 3, 0 = auto), "energy.nv" (16-byte vectors per
+ *         thread of variant 1, 0 = auto), "energy.pdl" (1 = launch with programmatic dependent launch).
  * dddm_launch_count returns the number of kernels this library has launched in this process.
  * ------------------------------------------------------------------------------------------ */
 int dddm_set_tuning(const char* key, int value);

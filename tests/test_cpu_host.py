@@ -59,9 +59,12 @@ def test_status_messages_and_validation(cabi):
 
 def test_kernel_plans(cabi):
     try:
-        assert cabi.describe_energy(128, 8, 3072).startswith("reg<f32,M=8,VEC=4")
-        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("reg<bf16,M=8,VEC=8")
+        assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
+        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
         assert cabi.describe_energy(512, 8, 2).startswith("reg<f32,M=8,VEC=1")
+        cabi.set_tuning("energy.variant", 1)
+        assert cabi.describe_energy(128, 8, 3072).startswith("reg<f32,M=8,VEC=4")
+        cabi.set_tuning("energy.variant", 0)
         assert cabi.describe_energy(128, 32, 3072).startswith("tile<f32,m=32>") and "tma-bulk" in cabi.describe_energy(
             128, 32, 3072)
         assert "ldg" in cabi.describe_energy(4, 16, 7)

@@ -34,7 +34,7 @@ def dev(cuda_device):
 
     _cabi.lib()
     yield cuda_device
-    for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl"):
+    for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl", "energy.threads"):
         _cabi.set_tuning(k, 0)
 
 
@@ -73,10 +73,10 @@ def _check_case(xh_np, x0_np, beta, dev, dtype=torch.float32, rel=FP32_REL, lam=
     gi = torch.tensor([-1.9], device=dev)
     gx, gx0 = ops.energy_terms_bwd(xh, x0, dist, gc, gi, beta, True)
     ref_gx, ref_gx0 = oracle.energy_terms_grad(xh64, x064, beta, 0.37, -1.9, want_x0=True)
-    if np.max(np.abs(ref_gx)) > 0:
-        assert _rel(gx.float().cpu().numpy(), ref_gx) <= rel
-    if np.max(np.abs(ref_gx0)) > 0:
-        assert _rel(gx0.float().cpu().numpy(), ref_gx0) <= rel
+    # one common scale for both gradients (a vanishing grad_x0 next to an O(1) grad_xhat is "zero")
+    gscale = max(np.max(np.abs(ref_gx)), np.max(np.abs(ref_gx0)), 1e-6)
+    assert np.max(np.abs(gx.float().cpu().numpy() - ref_gx)) <= rel * gscale
+    assert np.max(np.abs(gx0.float().cpu().numpy() - ref_gx0)) <= rel * gscale
 
 
 def test_golden_cases_fp32(dev, golden_energy):
@@ -100,9 +100,10 @@ def test_golden_values_against_reference_outputs(dev, golden_energy):
         assert np.max(np.abs(out - ref)) <= FP32_REL * np.max(np.abs(ref)), n
         one, zero = torch.ones(1, device=dev), torch.zeros(1, device=dev)
         gx, gx0 = ops.energy_terms_bwd(xh, x0, dist, one, zero, beta, True)
-        if np.max(np.abs(g[f"{n}/g_conf"])) > 0:
-            assert _rel(gx.cpu().numpy(), g[f"{n}/g_conf"]) <= FP32_REL, n
-            assert _rel(gx0.cpu().numpy(), g[f"{n}/g_conf_x0"]) <= FP32_REL, n
+        gscale = np.max(np.abs(g[f"{n}/g_conf"]))  # grad_x0 = -sum_i of these rows: same scale (it may cancel to ~0)
+        if gscale > 0:
+            assert np.max(np.abs(gx.cpu().numpy() - g[f"{n}/g_conf"])) <= FP32_REL * gscale, n
+            assert np.max(np.abs(gx0.cpu().numpy() - g[f"{n}/g_conf_x0"])) <= FP32_REL * gscale, n
         gx, _ = ops.energy_terms_bwd(xh, x0, dist, zero, one, beta, False)
         if np.max(np.abs(g[f"{n}/g_inter"])) > 0:
             assert _rel(gx.cpu().numpy(), g[f"{n}/g_inter"]) <= FP32_REL, n
@@ -182,14 +183,20 @@ def test_kernel_variants_agree(dev):
     loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(), 0.1, 1.0, 0.5)
     seen = set()
     try:
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             for cluster in (1, 2, 4, 8):
-                for nv in (1, 2):
+                for knob in (1, 2):
                     _cabi.set_tuning("energy.variant", variant)
                     _cabi.set_tuning("energy.cluster", cluster)
-                    _cabi.set_tuning("energy.nv", nv)
+                    _cabi.set_tuning("energy.nv", knob)
+                    _cabi.set_tuning("energy.threads", 32 * knob)
+                    nv = knob
+                    try:
+                        out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
+                    except _cabi.DDDMError as e:
+                        assert e.status == -4  # this plan does not cover the shape (e.g. register tile too wide)
+                        continue
                     seen.add(_cabi.describe_energy(16, 8, 3072))
-                    out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
                     assert abs(out[0] - loss) <= 2e-5 * abs(conf), (variant, cluster, nv)
                     assert _rel(g, grad) <= FP32_REL, (variant, cluster, nv, _rel(g, grad))
         for pdl in (0, 1):
@@ -200,9 +207,9 @@ def test_kernel_variants_agree(dev):
             out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
             assert _rel(g, grad) <= FP32_REL
     finally:
-        for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl"):
+        for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl", "energy.threads"):
             _cabi.set_tuning(k, 0)
-    assert len(seen) >= 8, seen
+    assert len(seen) >= 12, seen
 
 
 def test_deterministic_and_workspace_reuse(dev):

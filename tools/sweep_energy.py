@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Sweep the launch plan of the fused energy-score kernel on one GPU and print us/launch + GB/s.
+
+    python tools/sweep_energy.py [--B 128 --m 8 --D 3072 --dtype f32] [--configs "variant=1,cluster=8,nv=1;..."]
+
+Timing: CUDA graph of back-to-back launches over rotating buffer sets larger than 2x L2,
+CUDA events on the launch stream, median of 5 repetitions.
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from ddm_b200 import _cabi
+
+
+def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, nsets_override=0, nograd=False, null=False):
+    tdtype = torch.float32 if dtype == "f32" else torch.bfloat16
+    esz = 4 if dtype == "f32" else 2
+    dev = torch.device("cuda:0")
+    algo = (2 * B * m * D + B * D) * esz
+    nsets = nsets_override or max(4, -(-2 * 126 * 2**20 // algo) + 1)
+    fn = getattr(L, f"dddm_energy_fused_{dtype}")
+    sets = []
+    for s in range(nsets):
+        g = torch.Generator().manual_seed(s)
+        x0 = torch.randn(B, D, generator=g).clamp(-1, 1)
+        xh = x0[:, None] + 0.05 * torch.randn(B, m, D, generator=g)
+        sets.append((xh.to(tdtype).to(dev), x0.to(tdtype).to(dev), torch.empty(B, m, D, dtype=tdtype, device=dev),
+                     torch.zeros(4, device=dev), torch.full((1,), 0.5 * B, device=dev),
+                     torch.zeros(L.dddm_energy_workspace_bytes(B, m), dtype=torch.uint8, device=dev)))
+    stream = torch.cuda.Stream(dev)
+    side = torch.cuda.Stream(dev)
+    if two_streams:
+        nstreams = 2
+    sides = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
+
+    tnull = torch.rand(32, device=dev)
+
+    def launch(s, cs):
+        xh, x0, gr, out, w, ws = s
+        if null:  # launch-floor probe: a tiny single-CTA kernel in the same harness
+            _cabi.check(L.dddm_sigmoid_weight_sum_f32(tnull.data_ptr(), 0.0, None, w.data_ptr(), 32, cs))
+            return
+        _cabi.check(fn(xh.data_ptr(), x0.data_ptr(), w.data_ptr(), 1.0 / B, None if nograd else gr.data_ptr(),
+                       out.data_ptr(), ws.data_ptr(), B, m, D, 0.1, 1.0, cs))
+
+    chunk = nsets * max(1, 240 // nsets)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        if nstreams > 1:
+            main = torch.cuda.current_stream()
+            for sd in sides:
+                sd.wait_stream(main)
+            for i in range(chunk):
+                st = main if i % nstreams == 0 else sides[i % nstreams - 1]
+                launch(sets[i % nsets], st.cuda_stream)
+            for sd in sides:
+                main.wait_stream(sd)
+        else:
+            for i in range(chunk):
+                launch(sets[i % nsets], torch.cuda.current_stream().cuda_stream)
+    reps = max(1, iters // chunk)
+    times = []
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            graph.replay()
+        stream.synchronize()
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                graph.replay()
+            e1.record(stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3 / (reps * chunk))
+    us = sorted(times)[2]
+    return us, algo / us / 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=128)
+    ap.add_argument("--m", type=int, default=8)
+    ap.add_argument("--D", type=int, default=3072)
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--configs", default="")
+    ap.add_argument("--two-streams", action="store_true")
+    ap.add_argument("--sets", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=1)
+    ap.add_argument("--nograd", action="store_true")
+    ap.add_argument("--null", action="store_true")
+    a = ap.parse_args()
+    L = _cabi.lib()
+    if a.configs:
+        configs = [dict(kv.split("=") for kv in c.split(",")) for c in a.configs.split(";")]
+    else:
+        configs = [dict(variant=3, cluster=c, threads=t, pdl=1) for c, t in
+                   itertools.product((1, 2, 4, 8), (32, 64, 96, 128, 192, 256))]
+    for cfg in configs:
+        for k in ("variant", "cluster", "nv", "pdl", "threads"):
+            _cabi.set_tuning(f"energy.{k}", int(cfg.get(k, 0)))
+        desc = _cabi.describe_energy(a.B, a.m, a.D, a.dtype)
+        try:
+            us, gbs = time_config(L, a.B, a.m, a.D, a.dtype, two_streams=a.two_streams, nstreams=a.streams, nsets_override=a.sets,
+                                  nograd=a.nograd, null=a.null)
+            print(json.dumps({"cfg": cfg, "kernel": desc, "us": round(us, 3), "GBps": round(gbs, 1),
+                              "frac_of_6452": round(gbs / 6452.5, 3)}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"cfg": cfg, "kernel": desc, "error": str(e)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
