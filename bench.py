@@ -154,6 +154,10 @@ def main() -> None:
     ap.add_argument("--streams", type=int, default=4,
                     help="streams the independent steps are issued on round-robin inside the CUDA graph (1 = serialized)")
     ap.add_argument("--tune", default="", help="comma list key=value for dddm_set_tuning, e.g. energy.cluster=4")
+    ap.add_argument("--dit-steps", type=int, default=10,
+                    help="auxiliary: DP DiT training steps to time for the img/s figure (0 = skip)")
+    ap.add_argument("--dit-precision", default="bf16", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--sampler-samples", type=int, default=1024, help="auxiliary: Algorithm-2 samples (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -324,6 +328,41 @@ def main() -> None:
     h2d = (B * M * D + B * D) * esz + B * 4
     d2h = B * M * D * esz + 16
 
+    # ---- auxiliary (outside the timed region above): BASELINE configs 4 and 5 on the same GPUs ----
+    aux = {}
+    if args.dit_steps > 0:
+        from ddm_b200 import launcher
+
+        targs = launcher.build_parser().parse_args(["--synthetic", "--precision", args.dit_precision])
+        aux["dit_train"] = launcher.measure_throughput(targs, dev, world, steps=args.dit_steps, warmup=3)
+        aux["dit_train"]["config"] = ("DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
+                                      "data-parallel (DDP over NCCL), loss kernels K4+K2+K1 fused path")
+    if args.sampler_samples > 0:
+        from ddm_b200.backbones import DDDMDiT
+        from ddm_b200.sampling import sample_dddm
+
+        per = max(1, args.sampler_samples // world)
+        net = DDDMDiT().to(dev)
+        res = {}
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dit_precision == "bf16"):
+            for nsteps in (20, 100):
+                sample_dddm(net, per, steps=2, device=str(dev), data_shape=(3, 32, 32))
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                sample_dddm(net, per, steps=nsteps, device=str(dev), data_shape=(3, 32, 32))
+                a1.record()
+                a1.synchronize()
+                dt = a0.elapsed_time(a1) * 1e-3
+                if world > 1:
+                    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt)
+                res[f"steps{nsteps}"] = {"samples_per_s": per * world / dt, "seconds": dt}
+        aux["sampler"] = {"n_samples": per * world, "per_gpu": per, "model": "DDDMDiT(default)", **res}
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
@@ -364,6 +403,7 @@ def main() -> None:
                     "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait"},
             "gpu_launches": K * len(times) // len(times),
             "clocks": sampler.summary(),
+            "aux": aux,
             "all_region_ms_per_step": [1e3 * x / K for x in times],
         }
         print(json.dumps(line), flush=True)

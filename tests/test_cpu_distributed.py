@@ -1,0 +1,91 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel semantics the launcher relies on:
+the loss is a product of two batch means, so the logistic weight must be the GLOBAL mean — one float
+all-reduce of sum_b w(t_b) — for the rank-averaged gradient to equal the single-process global batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ddm_b200.training import _world
+
+        assert _world(None) == world
+        B, m, D, beta, lam, bias = 16, 4, 24, 0.1, 1.0, 0.2
+        gen = torch.Generator().manual_seed(0)  # the same global batch on every rank
+        x0 = torch.randn(B, D, generator=gen).clamp(-1, 1).double()
+        xh = x0[:, None] + 0.3 * torch.randn(B, m, D, generator=gen).double()
+        t = torch.rand(B, generator=gen).double()
+        per = B // world
+        sl = slice(rank * per, (rank + 1) * per)
+        # what the step does per rank: local w-sum -> all-reduce(SUM) -> W = sum / (world * per)
+        w_sum = torch.tensor([oracle.sigmoid_weight(t[sl].numpy(), bias).sum()], dtype=torch.float64)
+        local_w = float(w_sum) / per
+        dist.all_reduce(w_sum, op=dist.ReduceOp.SUM)
+        global_w = float(w_sum) / (world * per)
+        res = {}
+        for name, w in (("global", global_w), ("local", local_w)):
+            loss, conf, inter, grad = oracle.energy_loss(xh[sl].numpy(), x0[sl].numpy(), beta, lam, w)
+            # DDP averages parameter gradients over ranks; with d(param) = sum_b J_b^T dL/dxhat_b this is the
+            # rank-mean of the per-row gradients laid out in the global batch
+            full = torch.zeros(B, m, D, dtype=torch.float64)
+            full[sl] = torch.from_numpy(grad)
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)
+            full /= world
+            lt = torch.tensor([loss], dtype=torch.float64)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            res[name] = (full.numpy(), float(lt) / world)
+        if rank == 0:
+            gw = oracle.sigmoid_weight(t.numpy(), bias).mean()
+            ref_loss, _, _, ref_grad = oracle.energy_loss(xh.numpy(), x0.numpy(), beta, lam, gw)
+            np.savez(os.path.join(out_dir, "res.npz"), g_global=res["global"][0], l_global=res["global"][1],
+                     g_local=res["local"][0], l_local=res["local"][1], ref_grad=ref_grad, ref_loss=ref_loss,
+                     global_w=global_w, gw=gw)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_weight_makes_sharded_equal_global(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r = np.load(tmp_path / "res.npz")
+    assert abs(r["global_w"] - r["gw"]) < 1e-15
+    scale = np.max(np.abs(r["ref_grad"]))
+    assert np.max(np.abs(r["g_global"] - r["ref_grad"])) <= 1e-13 * scale
+    assert abs(r["l_global"] - r["ref_loss"]) <= 1e-13 * abs(r["ref_loss"])
+    # and the naive per-rank weight is NOT equivalent (this is the bug the all-reduce prevents)
+    assert np.max(np.abs(r["g_local"] - r["ref_grad"])) > 1e-3 * scale
+
+
+def test_launcher_flags_and_yaml_overlay(tmp_path):
+    from ddm_b200 import launcher
+
+    p = launcher.build_parser()
+    a = p.parse_args([])
+    # the reference's defaults (train_cifar10_dit.py:362-398)
+    assert (a.batch, a.lr, a.weight_decay, a.beta, a.lam, a.m, a.w_bias, a.grad_clip) == (128, 1e-4, 0.01, 0.1, 1.0, 8, 0.0, 1.0)
+    assert (a.embed_dim, a.depth, a.heads, a.time_embed, a.mlp_ratio, a.sample_steps, a.eps_churn) == (384, 8, 6, 256, 4.0, 20, 1.0)
+    cfg = tmp_path / "c.yaml"
+    cfg.write_text("batch: 256\nlr: 0.001\neps_churn: 0.0\n")
+    a = p.parse_args(["--config", str(cfg), "--lr", "0.5"])
+    launcher.apply_yaml(p, a)
+    assert a.batch == 256 and a.lr == 0.5 and a.eps_churn == 0.0  # CLI wins over YAML, YAML over defaults
+    cfg.write_text("no_such_key: 1\n")
+    a = p.parse_args(["--config", str(cfg)])
+    with pytest.raises(ValueError, match="Unknown config key"):
+        launcher.apply_yaml(p, a)
