@@ -260,3 +260,30 @@ def test_launch_counter(dev):
     before = _cabi.launch_count()
     ops.sigmoid_weight_sum(torch.rand(16, device=dev), 0.0)
     assert _cabi.launch_count() == before + 1
+
+
+def test_sharded_ranks_equal_global_batch(dev):
+    """Emulate R data-parallel ranks on one GPU by looping shards: with the global
+    w-sum (what the all-reduce produces) the rank-mean of per-shard K1 gradients is the global-batch gradient."""
+    from ddm_b200 import ops
+
+    B, m, D, R = 32, 8, 3072, 4
+    gen = torch.Generator().manual_seed(9)
+    x0 = torch.randn(B, D, generator=gen).clamp(-1, 1).to(dev)
+    xh = (x0[:, None].cpu() + 0.05 * torch.randn(B, m, D, generator=gen)).to(dev)
+    t = torch.rand(B, generator=gen).to(dev)
+    _, w_sum = ops.sigmoid_weight_sum(t, 0.0)
+    out_g, grad_g = ops.energy_fused(xh, x0, w_sum, 1.0 / B, 0.1, 1.0, True)
+    per = B // R
+    shard_sums = [ops.sigmoid_weight_sum(t[r * per:(r + 1) * per], 0.0)[1] for r in range(R)]
+    reduced = torch.stack(shard_sums).sum(dim=0)  # == all_reduce(SUM)
+    assert abs(float(reduced) - float(w_sum)) <= 1e-6 * float(w_sum)
+    grads, losses = [], []
+    for r in range(R):
+        sl = slice(r * per, (r + 1) * per)
+        o, g = ops.energy_fused(xh[sl].contiguous(), x0[sl].contiguous(), reduced, 1.0 / (R * per), 0.1, 1.0, True)
+        grads.append(g / R)  # DDP averages over ranks
+        losses.append(o[0])
+    got = torch.cat(grads, dim=0)
+    assert float((got - grad_g).abs().max()) <= 2e-6 * float(grad_g.abs().max())
+    assert abs(float(torch.stack(losses).mean()) - float(out_g[0])) <= 2e-6 * abs(float(out_g[0]))
