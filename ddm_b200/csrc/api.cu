@@ -259,8 +259,9 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     if (variant == 0 || variant == 3) {
         SmemPlan sp = plan_smem(m, D, es, al);
         if (sp.ok)
-            return snprintf(buf, buflen, "smem<%s,M=%d> tma-bulk f32x2 cluster=%d threads=%d slab_vecs=%d smem=%zu",
-                            dtype == 1 ? "bf16" : "f32", m, sp.cluster, sp.threads, sp.slab_vecs, sp.smem_bytes);
+            return snprintf(buf, buflen, "smem<%s,M=%d> tma-bulk f32x2 cluster=%d threads=%d slab_vecs=%d chunk_vecs=%d smem=%zu",
+                            dtype == 1 ? "bf16" : "f32", m, sp.cluster, sp.threads, sp.slab_vecs, sp.chunk_vecs,
+                            sp.smem_bytes);
         if (variant == 3) return snprintf(buf, buflen, "unsupported");
     }
     if (variant == 0 || variant == 1) {

@@ -24,6 +24,7 @@ namespace dddm {
 
 constexpr int kSmemMaxThreads = 256;  // compute threads per CTA; one extra control warp is added at launch
 constexpr int kSmemMaxCluster = 8;
+constexpr int kSmemMaxChunks = 8;  // column chunks of the tile, each with its own mbarrier
 
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
@@ -67,13 +68,13 @@ __host__ __device__ constexpr int pair_slot(int i, int j) {  // i < j
 
 template <typename T, int M>
 __global__ void __launch_bounds__(kSmemMaxThreads + 32, 1)
-energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size) {
+energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
     constexpr int P = M * (M + 1) / 2;
     constexpr int VEC = Elem<T>::kVec;
     constexpr int NP = Pairs<T>::kN;
     using WR = WarpReduce<P>;
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
     __shared__ float s_warp[kSmemMaxThreads / 32][P];
     __shared__ float s_cluster[kSmemMaxCluster][P];
     __shared__ float s_coef[P];
@@ -93,31 +94,36 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     const int nv = (int)max(0L, min((long)slab_vecs, nvec - v_begin));  // vectors in this CTA's slab
     const int row_bytes = slab_vecs * 16;
 
+    // The slab is staged in column chunks of chunk_vecs vectors (a multiple of the compute-thread
+    // count); chunk c signals s_bar[c], so pass 1 starts on chunk 0 while the rest is still in flight.
+    const int nchunks = (nv + chunk_vecs - 1) / chunk_vecs;
     if (control && lane == 0) {
-        mbar_init(&s_bar, 1);
+        for (int c = 0; c < nchunks; ++c) mbar_init(&s_bar[c], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     cudaGridDependencySynchronize();  // PDL: inputs may be produced by the previous kernel in the stream
-    if (control && nv > 0) {
-        const uint32_t bytes = (uint32_t)nv * 16u;
-        if (lane == 0) mbar_expect_tx(&s_bar, bytes * (uint32_t)(M + 1));
-        __syncwarp();
-        if (lane <= M) {
-            const T* src = (lane < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + lane) * p.D + v_begin * VEC
-                                      : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
-            tma_bulk_g2s(s_tile + (size_t)lane * row_bytes, src, bytes, &s_bar);
+    if (control) {
+        const T* src = (lane < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + lane) * p.D + v_begin * VEC
+                                  : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
+        for (int c = 0; c < nchunks; ++c) {
+            const int c0 = c * chunk_vecs;
+            const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
+            if (lane == 0) mbar_expect_tx(&s_bar[c], bytes * (uint32_t)(M + 1));
+            __syncwarp();
+            if (lane <= M)
+                tma_bulk_g2s(s_tile + (size_t)lane * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
         }
     }
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
-    if (nv > 0 && !control) mbar_wait(&s_bar, 0);
 
     // ---- pass 1 ----
     float2 acc2[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) acc2[q] = make_float2(0.f, 0.f);
     for (int v = control ? nv : tid; v < nv; v += nthr) {
+        if ((v - tid) % chunk_vecs == 0) mbar_wait(&s_bar[(v - tid) / chunk_vecs], 0);  // warp-uniform: entering a new chunk
         float2 x[M + 1][NP];
 #pragma unroll
         for (int r = 0; r <= M; ++r) lds_pairs<T>(s_tile + (size_t)r * row_bytes, v, x[r]);

@@ -26,6 +26,10 @@ SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16) {
         if (threads > 128) threads = 128;
         if (threads < 32) threads = 32;
     }
+    // column chunks: nv vectors per thread per chunk (tuning "energy.nv", default 2), at most kSmemMaxChunks chunks
+    int per_thread = (t.nv >= 1) ? t.nv : 2;
+    while ((slab + (long)threads * per_thread - 1) / ((long)threads * per_thread) > kSmemMaxChunks) ++per_thread;
+    s.chunk_vecs = threads * per_thread;
     s.cluster = cluster;
     s.threads = threads;
     s.slab_vecs = (int)slab;

@@ -15,7 +15,7 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
         configured = plan.smem_bytes;
     }
     return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
-                             p, plan.slab_vecs, plan.cluster);
+                             p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);
 }
 
 #define DDDM_DISPATCH_M_SMEM(T, p, plan, stream)                         \

@@ -7,7 +7,7 @@
 namespace dddm {
 struct SmemPlan {
     bool ok;
-    int cluster, threads, slab_vecs;
+    int cluster, threads, slab_vecs, chunk_vecs;
     size_t smem_bytes;
 };
 SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16);
