@@ -67,6 +67,7 @@ SIGNATURES = {
     "dddm_set_tuning": (c_int, [c_char_p, c_int]),
     "dddm_get_tuning": (c_int, [c_char_p]),
     "dddm_launch_count": (c_ulonglong, []),
+    "dddm_set_trace_buffer": (c_int, [c_void_p]),
     "dddm_energy_describe": (c_int, [c_int, c_int, c_int, c_int, c_char_p, c_int]),
 }
 

@@ -71,6 +71,7 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     auto* ws = static_cast<EnergyWorkspace*>(workspace);
     p.ticket = &ws->ticket;
     p.row_partials = reinterpret_cast<float*>(ws + 1);
+    p.trace = static_cast<unsigned long long*>(tuning().trace);
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
     // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel
@@ -234,6 +235,7 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.variant")) t.variant = value;
     else if (!strcmp(key, "energy.pdl")) t.pdl = value;
     else if (!strcmp(key, "energy.threads")) t.threads = value;
+    else if (!strcmp(key, "energy.ctas")) t.ctas = value;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -245,7 +247,12 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.variant")) return t.variant;
     if (!strcmp(key, "energy.pdl")) return t.pdl;
     if (!strcmp(key, "energy.threads")) return t.threads;
+    if (!strcmp(key, "energy.ctas")) return t.ctas;
     return DDDM_ERR_BAD_ARGUMENT;
+}
+int dddm_set_trace_buffer(void* device_buffer) {
+    tuning().trace = device_buffer;
+    return DDDM_OK;
 }
 unsigned long long dddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -20,7 +20,10 @@ struct Tuning {
     int nv = 0;       // 16-byte vectors per thread (0 = auto)
     int variant = 0;  // 0 auto, 1 register-resident, 2 generic smem/TMA tile, 3 TMA-staged packed-fp32 (m <= 8)
     int threads = 0;  // threads per CTA for variant 3 (0 = auto)
-    int pdl = 0;      // programmatic dependent launch
+    int pdl = 1;      // programmatic dependent launch (the prologue overlaps the previous kernel's tail; every
+                      // kernel waits on cudaGridDependencySynchronize() before touching global memory)
+    int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
+    void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)
 };
 Tuning& tuning();
 
@@ -58,6 +61,18 @@ __device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
                  "r"(v.w)
                  : "memory");
+}
+
+__device__ __forceinline__ void stg_stream8(void* p, const uint2& v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream4(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
@@ -129,6 +144,30 @@ __device__ __forceinline__ float pow_deriv(float d2, const PowSpec& s) {
     if (s.mode == 2) return 1.0f;
     float x = d2 + kPowEps;
     return s.mode == 1 ? 0.5f * rsqrtf(x) : s.half_beta * powf(x, s.half_beta - 1.0f);
+}
+
+// f(d2) and f'(d2) together, off the slow path: powf + an IEEE division cost ~600 ns of dependent
+// latency per row on the kernel's critical path (tools/trace_energy.py).  Here x^h = 2^(h*log2 x) with
+// the 1-ulp log2f, the rounding error of the product h*log2(x) carried as a first-order correction,
+// and f' = h * f / x through the reciprocal unit.  Relative error <= ~1e-6 for beta < 2 over the whole
+// range [1e-12, 1e30] (|log2 x| < 128), ~1e-7 for beta = 0.1 — inside the 1e-5 budget of the path.
+__device__ __forceinline__ void pow_value_deriv(float d2, const PowSpec& s, float& val, float& der) {
+    if (s.mode == 2) {
+        val = d2;
+        der = 1.0f;
+        return;
+    }
+    const float x = d2 + kPowEps;
+    if (s.mode == 1) {
+        val = sqrtf(x);
+        der = 0.5f * __fdividef(val, x);
+        return;
+    }
+    const float l = log2f(x);
+    const float e_hi = s.half_beta * l;
+    const float e_lo = fmaf(s.half_beta, l, -e_hi);
+    val = exp2f(e_hi) * fmaf(e_lo, 0.693147181f, 1.0f);
+    der = s.half_beta * __fdividef(val, x);
 }
 
 // ---- warp-level reduction of P per-lane partial sums ----------------------------------------

@@ -28,6 +28,7 @@ struct EnergyParams {
     float lam;
     PowSpec pw;
     int mode;
+    unsigned long long* trace;  // diagnostics: 8 globaltimer stamps per CTA, or null (dddm_set_trace_buffer)
 };
 
 struct EnergyWorkspace {  // layout of the caller-provided workspace
@@ -109,18 +110,27 @@ __device__ __forceinline__ void cluster_wait_acquire() {
 
 // ---- deterministic cross-row reduction, executed by the last arriving row ------------------
 // Called by ONE warp of the CTA that owns row b after its per-row sums are known.
+//
+// No __threadfence(): a GPU-scope fence issued while the other warps of the SM stream the gradient
+// out costs ~1 us (measured with tools/trace_energy.py) and sat on the kernel's critical path.
+// Instead the row's two sums are published with ONE returning 64-bit atomic exchange (performed at
+// L2, the point of coherence), and the ticket increment consumes the exchange's return value, so it
+// cannot be issued before the exchange has been performed.  The last arriver therefore reads every
+// row's sums (ld.global.cg = L2) after they are in L2.  Both sums are non-negative (sign bits are
+// cleared, which also canonicalises NaNs), hence bit 63 of whatever the slot held before — zeros
+// from the initial memset or an earlier launch's sums — is 0 and the increment is exactly 1.
 __device__ __forceinline__ void finish_row(const EnergyParams& p, int b, float conf_row, float inter_row, float W,
                                            int lane) {
     unsigned old = 0;
     if (lane == 0) {
-        reinterpret_cast<float2*>(p.row_partials)[b] = make_float2(conf_row, inter_row);
-        __threadfence();
-        old = atomicAdd(p.ticket, 1u);
+        const unsigned long long packed = (unsigned long long)(__float_as_uint(conf_row) & 0x7fffffffu) |
+                                          ((unsigned long long)(__float_as_uint(inter_row) & 0x7fffffffu) << 32);
+        const unsigned long long prev = atomicExch(reinterpret_cast<unsigned long long*>(p.row_partials) + b, packed);
+        old = atomicAdd(p.ticket, 1u + (unsigned)(prev >> 63));
     }
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old != (unsigned)(p.B - 1)) return;
-    // last row: every row's partials are visible after the fence; sum them in a fixed order
-    __threadfence();
+    // last row: sum every row's partials in a fixed order
     float c = 0.f, i = 0.f;
     for (int r = lane; r < p.B; r += 32) {
         float2 v = __ldcg(reinterpret_cast<const float2*>(p.row_partials) + r);

@@ -22,43 +22,53 @@
 
 namespace dddm {
 
-constexpr int kSmemMaxThreads = 256;  // compute threads per CTA; one extra control warp is added at launch
+constexpr int kSmemMaxThreads = 128;  // compute threads per CTA (one warp per SM sub-partition); a control warp is added at launch
 constexpr int kSmemMaxCluster = 8;
 constexpr int kSmemMaxChunks = 8;  // column chunks of the tile, each with its own mbarrier
 
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
-// 16-byte vector in shared memory -> packed fp32 pairs (2 pairs for fp32, 4 for bf16)
-template <typename T>
-struct Pairs {
-    static constexpr int kN = (sizeof(T) == 4) ? 2 : 4;
-    float2 v[kN];
+// The unit of work of a thread is a "step" of COLS consecutive columns = COLS/2 packed-fp32 pairs.
+// COLS = 4 keeps instruction count lowest (one LDS.128 per row for fp32); COLS = 2 halves the live
+// registers so that more CTAs fit an SM (used for bf16, whose small tile leaves registers as the limit).
+template <typename T, int COLS>
+struct Step {
+    static_assert(COLS == 2 || COLS == 4, "2 or 4 columns per step");
+    static constexpr int kPairs = COLS / 2;
+    static constexpr int kBytes = COLS * (int)sizeof(T);
+    static constexpr int kPerVec = 16 / kBytes;  // steps per 16-byte vector
 };
-template <typename T>
-__device__ __forceinline__ void lds_pairs(const unsigned char* row, int vec, float2 (&out)[Pairs<T>::kN]) {
-    if constexpr (sizeof(T) == 4) {
-        const float4 r = reinterpret_cast<const float4*>(row)[vec];
+template <typename T, int COLS>
+__device__ __forceinline__ void lds_step(const unsigned char* row, int q, float2 (&out)[COLS / 2]) {
+    if constexpr (sizeof(T) == 4 && COLS == 4) {
+        const float4 r = reinterpret_cast<const float4*>(row)[q];
         out[0] = make_float2(r.x, r.y);
         out[1] = make_float2(r.z, r.w);
-    } else {
-        const uint4 r = reinterpret_cast<const uint4*>(row)[vec];
+    } else if constexpr (sizeof(T) == 4) {
+        out[0] = reinterpret_cast<const float2*>(row)[q];
+    } else if constexpr (COLS == 4) {
+        const uint2 r = reinterpret_cast<const uint2*>(row)[q];
         out[0] = make_float2(bf16lo(r.x), bf16hi(r.x));
         out[1] = make_float2(bf16lo(r.y), bf16hi(r.y));
-        out[2] = make_float2(bf16lo(r.z), bf16hi(r.z));
-        out[3] = make_float2(bf16lo(r.w), bf16hi(r.w));
+    } else {
+        const uint32_t r = reinterpret_cast<const uint32_t*>(row)[q];
+        out[0] = make_float2(bf16lo(r), bf16hi(r));
     }
 }
-template <typename T>
-__device__ __forceinline__ void stg_pairs(T* __restrict__ dst, long elem, const float2 (&g)[Pairs<T>::kN]) {
-    uint4 r;
-    if constexpr (sizeof(T) == 4) {
+template <typename T, int COLS>
+__device__ __forceinline__ void stg_step(T* __restrict__ dst, const float2 (&g)[COLS / 2]) {
+    if constexpr (sizeof(T) == 4 && COLS == 4) {
+        uint4 r;
         r.x = __float_as_uint(g[0].x); r.y = __float_as_uint(g[0].y);
         r.z = __float_as_uint(g[1].x); r.w = __float_as_uint(g[1].y);
+        stg_stream16(dst, r);
+    } else if constexpr (sizeof(T) == 4) {
+        stg_stream8(dst, make_uint2(__float_as_uint(g[0].x), __float_as_uint(g[0].y)));
+    } else if constexpr (COLS == 4) {
+        stg_stream8(dst, make_uint2(pack_bf16x2(g[0].x, g[0].y), pack_bf16x2(g[1].x, g[1].y)));
     } else {
-        r.x = pack_bf16x2(g[0].x, g[0].y); r.y = pack_bf16x2(g[1].x, g[1].y);
-        r.z = pack_bf16x2(g[2].x, g[2].y); r.w = pack_bf16x2(g[3].x, g[3].y);
+        stg_stream4(dst, pack_bf16x2(g[0].x, g[0].y));
     }
-    stg_stream16(dst + elem, r);
 }
 
 template <int M>
@@ -66,13 +76,20 @@ __host__ __device__ constexpr int pair_slot(int i, int j) {  // i < j
     return M + i * M - i * (i + 1) / 2 + (j - i - 1);
 }
 
-template <typename T, int M>
-__global__ void __launch_bounds__(kSmemMaxThreads + 32, 1)
+// Optional in-kernel timeline (diagnostics; tools/trace_energy.py): 16 globaltimer stamps per CTA.
+#define DDDM_TRACE(slot)                                                                              \
+    do {                                                                                              \
+        if (p.trace != nullptr) p.trace[((long)b * cluster_size + rank) * 16 + (slot)] = globaltimer_ns(); \
+    } while (0)
+
+template <typename T, int M, int COLS, int MIN_CTAS>
+__global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
 energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
     constexpr int P = M * (M + 1) / 2;
     constexpr int VEC = Elem<T>::kVec;
-    constexpr int NP = Pairs<T>::kN;
+    constexpr int U = Step<T, COLS>::kPerVec;
+    constexpr int NP = Step<T, COLS>::kPairs;
     using WR = WarpReduce<P>;
     __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
     __shared__ float s_warp[kSmemMaxThreads / 32][P];
@@ -87,22 +104,30 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     const bool control = warp == nwarps;
     const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : 0;
     const int b = blockIdx.y;
+    if (tid == 0) DDDM_TRACE(0);
     if (cluster_size > 1) cluster_arrive_relaxed();  // phase 0: "my shared memory exists"
 
     const long nvec = p.D / VEC;
     const long v_begin = (long)rank * slab_vecs;
-    const int nv = (int)max(0L, min((long)slab_vecs, nvec - v_begin));  // vectors in this CTA's slab
+    const int nv = (int)max(0L, min((long)slab_vecs, nvec - v_begin));  // 16-byte vectors in this CTA's slab
+    const int nq = nv * U;                                              // steps (COLS columns each) in this CTA's slab
     const int row_bytes = slab_vecs * 16;
 
     // The slab is staged in column chunks of chunk_vecs vectors (a multiple of the compute-thread
     // count); chunk c signals s_bar[c], so pass 1 starts on chunk 0 while the rest is still in flight.
     const int nchunks = (nv + chunk_vecs - 1) / chunk_vecs;
+    const int chunk_q = chunk_vecs * U;
+    if (control) {  // rows of absent compute warps stay zero: the cross-warp sum always adds all 4 rows
+        for (int w = nwarps; w < kSmemMaxThreads / 32; ++w)
+            for (int s = lane; s < P; s += 32) s_warp[w][s] = 0.f;
+    }
     if (control && lane == 0) {
         for (int c = 0; c < nchunks; ++c) mbar_init(&s_bar[c], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the TMA (async proxy)
     }
     __syncthreads();
     cudaGridDependencySynchronize();  // PDL: inputs may be produced by the previous kernel in the stream
+    if (tid == 0) DDDM_TRACE(1);
     if (control) {
         const T* src = (lane < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + lane) * p.D + v_begin * VEC
                                   : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
@@ -114,19 +139,27 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             if (lane <= M)
                 tma_bulk_g2s(s_tile + (size_t)lane * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
         }
+        if (lane == 0) DDDM_TRACE(6);
     }
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
+    // gradient prefactors (independent of the distances: computed while the tile is in flight)
+    const float nb = (float)p.B * (float)M;
+    const float pre_conf = 2.0f * W / nb;
+    const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
-    // ---- pass 1 ----
+    // ---- pass 1: squared distances, COLS columns per thread per step ----
     float2 acc2[P];
 #pragma unroll
-    for (int q = 0; q < P; ++q) acc2[q] = make_float2(0.f, 0.f);
-    for (int v = control ? nv : tid; v < nv; v += nthr) {
-        if ((v - tid) % chunk_vecs == 0) mbar_wait(&s_bar[(v - tid) / chunk_vecs], 0);  // warp-uniform: entering a new chunk
+    for (int s = 0; s < P; ++s) acc2[s] = make_float2(0.f, 0.f);
+    for (int q = control ? nq : tid; q < nq; q += nthr) {
+        if ((q - tid) % chunk_q == 0) {  // warp-uniform: entering a new chunk
+            mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+            if (tid == 0 && q == 0) DDDM_TRACE(2);
+        }
         float2 x[M + 1][NP];
 #pragma unroll
-        for (int r = 0; r <= M; ++r) lds_pairs<T>(s_tile + (size_t)r * row_bytes, v, x[r]);
+        for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
 #pragma unroll
         for (int h = 0; h < NP; ++h) {
 #pragma unroll
@@ -143,48 +176,45 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
                 }
         }
     }
+    if (tid == 0) DDDM_TRACE(3);
+    if (tid == nthr - 32) DDDM_TRACE(11);
     float acc[WR::kPadded];
 #pragma unroll
-    for (int q = 0; q < WR::kPadded; ++q) acc[q] = (q < P) ? acc2[q < P ? q : 0].x + acc2[q < P ? q : 0].y : 0.f;
+    for (int s = 0; s < WR::kPadded; ++s) acc[s] = (s < P) ? acc2[s < P ? s : 0].x + acc2[s < P ? s : 0].y : 0.f;
     if (!control) WR::run(acc, s_warp[warp], lane);
+    if (tid == 0) DDDM_TRACE(8);
     __syncthreads();
+    if (tid == 0) DDDM_TRACE(9);
 
-    // ---- cross-warp and cross-CTA sums, fixed order ----
+    // ---- cross-warp and cross-CTA sums, fixed order; one thread per distance ----
+    static_assert(kSmemMaxThreads / 32 == 4, "fixed 4-row cross-warp sum");
     if (cluster_size > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster_wait_acquire();  // phase 0 complete: every CTA of the cluster is running
-        for (int q = tid; q < P; q += blockDim.x) {
-            float t = 0.f;
-            for (int w = 0; w < nwarps; ++w) t += s_warp[w][q];
-            for (int r = 0; r < cluster_size; ++r) cluster.map_shared_rank(&s_cluster[0][0], r)[rank * P + q] = t;
+        if (tid < P) {
+            const float t = (s_warp[0][tid] + s_warp[1][tid]) + (s_warp[2][tid] + s_warp[3][tid]);
+            for (int r = 0; r < cluster_size; ++r) cluster.map_shared_rank(&s_cluster[0][0], r)[rank * P + tid] = t;
         }
         cluster_arrive_release();
         cluster_wait_acquire();
     }
-    for (int q = tid; q < P; q += blockDim.x) {
+    if (tid < P) {
+        const int s = tid;
         float total = 0.f;
         if (cluster_size > 1) {
-            for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][q];
+            for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][s];
         } else {
-            for (int w = 0; w < nwarps; ++w) total += s_warp[w][q];
+            total = (s_warp[0][s] + s_warp[1][s]) + (s_warp[2][s] + s_warp[3][s]);
         }
-        // f(d2) and f'(d2) with a single transcendental: f' = (beta/2) f / (d2 + eps)
         float val, der;
-        if (p.pw.mode == 2) {
-            val = total;
-            der = 1.0f;
-        } else {
-            const float xe = total + kPowEps;
-            val = (p.pw.mode == 1) ? sqrtf(xe) : powf(xe, p.pw.half_beta);
-            der = p.pw.half_beta * __fdiv_rn(val, xe);
-        }
-        s_val[q] = val;
-        const float cl = p.lam / (2.0f * (float)(M - 1));
-        const float nb = (float)p.B * (float)M;
-        s_coef[q] = (q < M) ? 2.0f * W / nb * der : -4.0f * W * cl / (nb * (float)(M - 1)) * der;
-        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + q] = total;
+        pow_value_deriv(total, p.pw, val, der);
+        s_val[s] = val;
+        s_coef[s] = ((s < M) ? pre_conf : pre_pair) * der;
+        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
     }
+    if (tid == 0) DDDM_TRACE(10);
     __syncthreads();
+    if (tid == 0) DDDM_TRACE(4);
 
     // ---- cross-row reduction: the control warp of the row's first CTA, concurrently with pass 2 ----
     if (control) {
@@ -197,40 +227,44 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             c = warp_sum(c);
             it = 2.0f * warp_sum(it);
             finish_row(p, b, c, it, W, lane);
+            if (lane == 0) DDDM_TRACE(7);
         }
         return;
     }
 
-    // ---- pass 2 ----
-    if (p.grad_xhat != nullptr && nv > 0) {
+    // ---- pass 2: gradient rows from the same tile.  Every pair difference x_i - x_j is formed once and
+    //      feeds both rows (g_i += k d, g_j -= k d; the negation is an operand modifier of FFMA2). ----
+    if (p.grad_xhat != nullptr && nq > 0) {
         float2 K2[P];
 #pragma unroll
-        for (int q = 0; q < P; ++q) {
-            const float k = s_coef[q];
-            K2[q] = make_float2(k, k);
+        for (int s = 0; s < P; ++s) {
+            const float k = s_coef[s];
+            K2[s] = make_float2(k, k);
         }
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
-        for (int v = tid; v < nv; v += nthr) {
-            float2 x[M + 1][NP];
+        for (int q = tid; q < nq; q += nthr) {
+            float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
-            for (int r = 0; r <= M; ++r) lds_pairs<T>(s_tile + (size_t)r * row_bytes, v, x[r]);
+            for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                float2 g[NP];
+            for (int h = 0; h < NP; ++h) {
 #pragma unroll
-                for (int h = 0; h < NP; ++h) g[h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
+                for (int i = 0; i < M; ++i) g[i][h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    if (j == i) continue;
-                    const int q = (i < j) ? pair_slot<M>(i, j) : pair_slot<M>(j, i);
+                for (int i = 0; i < M; ++i)
 #pragma unroll
-                    for (int h = 0; h < NP; ++h) g[h] = __ffma2_rn(K2[q], sub2(x[i][h], x[j][h]), g[h]);
-                }
-                stg_pairs<T>(grow + (long)i * p.D, (long)v * VEC, g);
+                    for (int j = i + 1; j < M; ++j) {
+                        const float2 d = sub2(x[i][h], x[j][h]);
+                        const float2 k = K2[pair_slot<M>(i, j)];
+                        g[i][h] = __ffma2_rn(k, d, g[i][h]);
+                        g[j][h] = __ffma2_rn(make_float2(-k.x, -k.y), d, g[j][h]);
+                    }
             }
+#pragma unroll
+            for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
         }
     }
-
+    if (tid == 0) DDDM_TRACE(5);
 }
 
 }  // namespace dddm

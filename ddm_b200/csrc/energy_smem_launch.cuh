@@ -7,12 +7,20 @@ namespace dddm {
 
 template <typename T, int M>
 int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
-    auto kernel = energy_fused_smem_kernel<T, M>;
-    static size_t configured = 0;
-    if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > configured) {
+    // fp32: the 110 KB tile limits an SM to 2 CTAs, so 4 columns per step (fewest instructions);
+    // bf16: the tile is half as big, registers are the limit -> 2 columns per step, 3 CTAs per SM.
+    constexpr int kCols = (sizeof(T) == 4) ? 4 : 2;
+    constexpr int kMinCtas = (sizeof(T) == 4) ? 2 : 3;
+    auto kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas>;
+    if constexpr (sizeof(T) == 2) {
+        if (tuning().ctas == 4) kernel = energy_fused_smem_kernel<T, M, kCols, 4>;  // experiment: tighter register cap
+    }
+    static size_t configured[2] = {0, 0};
+    size_t& conf = configured[tuning().ctas == 4 ? 1 : 0];
+    if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
         if (e != cudaSuccess) return (int)e;
-        configured = plan.smem_bytes;
+        conf = plan.smem_bytes;
     }
     return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
                              p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);

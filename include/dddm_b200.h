@@ -162,12 +162,16 @@ int dddm_last_error(void);
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
  *         3 = TMA-staged packed-fp32 kernel for m <= 8), "energy.cluster" (CTAs per row, 0 = auto),
  *         "energy.threads" (threads per CTA of variant 3, 0 = auto), "energy.nv" (16-byte vectors per
- *         thread of variant 1, 0 = auto), "energy.pdl" (1 = launch with programmatic dependent launch).
+ *         thread of variant 1, 0 = auto), "energy.pdl" (programmatic dependent launch, default 1), "energy.ctas" (experiment).
  * dddm_launch_count returns the number of kernels this library has launched in this process.
  * ------------------------------------------------------------------------------------------ */
 int dddm_set_tuning(const char* key, int value);
 int dddm_get_tuning(const char* key);
 unsigned long long dddm_launch_count(void);
+/* Diagnostics: while a device buffer of >= B * cluster * 16 uint64 is set, the TMA-staged energy kernel writes up
+ * to 16 %globaltimer stamps per CTA (entry, inputs ready, first chunk landed, pass 1 done, coefficients ready,
+ * pass 2 done, TMA issued, row finished).  NULL (the default) disables it.  tools/trace_energy.py. */
+int dddm_set_trace_buffer(void* device_buffer);
 /* Describes the kernel variant the current tuning would pick for a shape, e.g.
  * "reg<f32,M=8,VEC=4,NV=1> cluster=8 threads=96". Returns chars written (excluding NUL). */
 int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen);
