@@ -75,7 +75,8 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
     // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel
-    // (m <= 8, any alignment) > chunked smem-tile kernel (any m <= 64)
+    // (m <= 8, any alignment) > blocked packed-fp32 kernel (m = 16, 32, aligned rows) > chunked smem-tile
+    // kernel (any m <= 64)
     const int variant = tuning().variant;
     if (variant == 0 || variant == 3) {
         SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al);
@@ -86,6 +87,11 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
         RegPlan plan = plan_reg(p.m, p.D, (int)sizeof(T), al, false);
         if (plan.ok) return launch_energy_reg<T>(p, plan, stream);
         if (variant == 1) return DDDM_ERR_UNSUPPORTED;
+    }
+    if (variant == 0 || variant == 4) {
+        SmemPlan bp = plan_blk(p.m, p.D, (int)sizeof(T), al);
+        if (bp.ok) return launch_energy_blk<T>(p, bp, stream);
+        if (variant == 4) return DDDM_ERR_UNSUPPORTED;
     }
     TilePlan tp = plan_tile(p.m, p.D, (int)sizeof(T), al);
     if (!tp.ok) return DDDM_ERR_UNSUPPORTED;
@@ -278,6 +284,13 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
                          r.vec, r.nv, r.cluster, r.threads);
             return n;
         }
+    }
+    if (variant == 0 || variant == 4) {
+        SmemPlan bp = plan_blk(m, D, es, al);
+        if (bp.ok)
+            return snprintf(buf, buflen, "blk<%s,M=%d> tma-bulk f32x2 cluster=%d threads=%d slab_vecs=%d chunk_vecs=%d smem=%zu",
+                            dtype == 1 ? "bf16" : "f32", m, bp.cluster, bp.threads, bp.slab_vecs, bp.chunk_vecs, bp.smem_bytes);
+        if (variant == 4) return snprintf(buf, buflen, "unsupported");
     }
     TilePlan t = plan_tile(m, D, es, al);
     if (t.ok)

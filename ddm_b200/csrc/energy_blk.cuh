@@ -1,0 +1,295 @@
+// energy_blk.cuh — TMA-staged, packed-fp32 energy-score kernel for m = 16 and m = 32 (BASELINE config 3).
+//
+// Same skeleton as energy_smem.cuh (one cluster per minibatch row, CTAs split D, a control warp stages
+// the (m+1) x slab tile with chunked 1-D TMA bulk copies, 128 compute threads, PDL, fence-free row
+// publication), but the m(m+1)/2 squared distances no longer fit a thread's registers, so the two
+// passes are organised differently:
+//   pass 1  "sweeps" over 8x8 blocks of the pair matrix: a thread walks its columns once per sweep with
+//           the block's 64 (off-diagonal block) or 2 x 36 (two diagonal blocks incl. the confinement
+//           column) accumulators in registers, differences and squares in packed fp32 (FADD2/FFMA2);
+//           each sweep ends in a butterfly warp reduction into the per-warp pair table;
+//   coeffs  f and f' for all P distances (all threads), K as a full m x m table in shared memory;
+//   pass 2  column owner: a thread keeps all m gradient rows of its 2 columns in registers (m float2),
+//           streams the coefficients from shared memory (LDS.128, uniform address = broadcast) and forms
+//           every difference x_i - x_j once for both rows (g_i += k d, g_j -= k d).
+// At m = 32 the path is fp32-CUDA-core bound (1.8 GFLOP per launch at B = 128, D = 3072); the direct
+// difference form is kept because the Gram form loses the fp32 tolerance.
+// Reference arithmetic: dddm/losses.py:5-25 (terms), dddm/training.py:84-85 (loss).
+#pragma once
+
+#include <cooperative_groups.h>
+
+#include "energy_smem.cuh"
+
+namespace dddm {
+
+constexpr int kBlkCols = 2;      // columns per thread step in both passes
+constexpr int kBlkMaxSplit = 2;  // column splits of pass 1 (pair tables in shared memory)
+
+__device__ __forceinline__ void unpair8(int idx, int& i, int& j) {  // inverse of pair_slot<8>(i, j) - 8
+    i = 0;
+    int left = idx;
+    while (left >= 7 - i) {
+        left -= 7 - i;
+        ++i;
+    }
+    j = i + 1 + left;
+}
+
+template <typename T, int M, int MIN_CTAS>
+__global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
+energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
+    namespace cg = cooperative_groups;
+    static_assert(M == 16 || M == 32, "blocked kernel: m in {16, 32} (diagonal blocks are swept in pairs)");
+    constexpr int P = M * (M + 1) / 2;
+    constexpr int VEC = Elem<T>::kVec;
+    constexpr int COLS = kBlkCols;
+    constexpr int U = Step<T, COLS>::kPerVec;
+    constexpr int NB = M / 8;
+    using WRD = WarpReduce<72>;
+    using WRO = WarpReduce<64>;
+    __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
+    __shared__ __align__(16) float s_K[M * M];   // K[i][j], j > i used
+    __shared__ __align__(16) float s_A[M];       // confinement coefficients
+    __shared__ float s_val[P];
+    __shared__ float s_tmp[kSmemMaxThreads / 32][72];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    // dynamic layout: tile [(M+1) x slab_vecs x 16] | s_warp [nsplit][P] (one pair table per column split)
+    const int row_bytes = slab_vecs * 16;
+    unsigned char* s_tile = s_dyn;
+    float* s_warp = reinterpret_cast<float*>(s_dyn + (size_t)(M + 1) * row_bytes);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x >> 5) - 1;
+    const int nthr = nwarps * 32;
+    const bool control = warp == nwarps;
+    const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    const int b = blockIdx.y;
+    if (cluster_size > 1) cluster_arrive_relaxed();
+
+    const long nvec = p.D / VEC;
+    const long v_begin = (long)rank * slab_vecs;
+    const int nv = (int)max(0L, min((long)slab_vecs, nvec - v_begin));
+    const int nq = nv * U;
+    const int nchunks = (nv + chunk_vecs - 1) / chunk_vecs;
+    const int chunk_q = chunk_vecs * U;
+    for (int s = tid; s < kBlkMaxSplit * P; s += blockDim.x) s_warp[s] = 0.f;
+    if (control && lane == 0) {
+        for (int c = 0; c < nchunks; ++c) mbar_init(&s_bar[c], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    cudaGridDependencySynchronize();
+    if (control) {
+        // rows 0..M-1 = draws, row M = x0; lanes stride the rows (M + 1 may exceed 32)
+        for (int c = 0; c < nchunks; ++c) {
+            const int c0 = c * chunk_vecs;
+            const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
+            if (lane == 0) mbar_expect_tx(&s_bar[c], bytes * (uint32_t)(M + 1));
+            __syncwarp();
+            for (int r = lane; r <= M; r += 32) {
+                const T* src = (r < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + r) * p.D + v_begin * VEC
+                                       : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
+                tma_bulk_g2s(s_tile + (size_t)r * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
+            }
+        }
+    }
+    const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
+    cudaTriggerProgrammaticLaunchCompletion();
+    const float nb = (float)p.B * (float)M;
+    const float pre_conf = 2.0f * W / nb;
+    const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
+
+    // ---- pass 1: block sweeps.  A work unit = (sweep, column split); units are dealt to the warps round-robin, the
+    //      warp's lanes stride the unit's columns, so every distance of a split is produced by exactly one warp. ----
+    constexpr int NSWEEP = NB / 2 + NB * (NB - 1) / 2;  // M = 16: 2, M = 32: 8
+    const int nsplit = max(1, nwarps / NSWEEP);         // column splits (M = 16 with 4 warps: 2)
+    if (!control) {
+        const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
+        int waited = -1;  // chunks this thread has already waited for
+        for (int unit = warp; unit < NSWEEP * nsplit; unit += nwarps) {
+            const int sweep = unit / nsplit, split = unit - sweep * nsplit;
+            const int q_begin = (int)((long)nq * split / nsplit), q_end = (int)((long)nq * (split + 1) / nsplit);
+            float* table = s_warp + split * P;
+            if (sweep < NB / 2) {
+                // two diagonal blocks: 8 confinement + 28 pair accumulators each
+                const int rA = 16 * sweep, rB = rA + 8;
+                float2 acc2[72];
+#pragma unroll
+                for (int s = 0; s < 72; ++s) acc2[s] = make_float2(0.f, 0.f);
+                for (int q = q_begin + lane; q < q_end; q += 32) {
+                    for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
+                    float2 x0v[1], xa[8][1], xb[8][1];
+                    lds_step<T, COLS>(x0row, q, x0v);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        lds_step<T, COLS>(s_tile + (size_t)(rA + r) * row_bytes, q, xa[r]);
+                        lds_step<T, COLS>(s_tile + (size_t)(rB + r) * row_bytes, q, xb[r]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 da = sub2(xa[i][0], x0v[0]);
+                        acc2[i] = __ffma2_rn(da, da, acc2[i]);
+                        const float2 db = sub2(xb[i][0], x0v[0]);
+                        acc2[36 + i] = __ffma2_rn(db, db, acc2[36 + i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < 8; ++j) {
+                            const float2 da = sub2(xa[i][0], xa[j][0]);
+                            acc2[pair_slot<8>(i, j)] = __ffma2_rn(da, da, acc2[pair_slot<8>(i, j)]);
+                            const float2 db = sub2(xb[i][0], xb[j][0]);
+                            acc2[36 + pair_slot<8>(i, j)] = __ffma2_rn(db, db, acc2[36 + pair_slot<8>(i, j)]);
+                        }
+                }
+                float acc[WRD::kPadded];
+#pragma unroll
+                for (int s = 0; s < 72; ++s) acc[s] = acc2[s].x + acc2[s].y;
+                WRD::run(acc, s_tmp[warp], lane);
+                __syncwarp();
+                for (int l = lane; l < 72; l += 32) {
+                    const int blk = l / 36, ll = l - 36 * blk, r0 = blk ? rB : rA;
+                    int slot;
+                    if (ll < 8) {
+                        slot = r0 + ll;
+                    } else {
+                        int i, j;
+                        unpair8(ll - 8, i, j);
+                        slot = pair_slot<M>(r0 + i, r0 + j);
+                    }
+                    table[slot] = s_tmp[warp][l];
+                }
+                __syncwarp();
+            } else {
+                // off-diagonal 8x8 block (bi < bj), enumerated row-major
+                int k = sweep - NB / 2, bi = 0;
+                while (k >= NB - 1 - bi) {
+                    k -= NB - 1 - bi;
+                    ++bi;
+                }
+                const int rI = 8 * bi, rJ = 8 * (bi + 1 + k);
+                float2 acc2[64];
+#pragma unroll
+                for (int s = 0; s < 64; ++s) acc2[s] = make_float2(0.f, 0.f);
+                for (int q = q_begin + lane; q < q_end; q += 32) {
+                    for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
+                    float2 xi[8][1], xj[8][1];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        lds_step<T, COLS>(s_tile + (size_t)(rI + r) * row_bytes, q, xi[r]);
+                        lds_step<T, COLS>(s_tile + (size_t)(rJ + r) * row_bytes, q, xj[r]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float2 d = sub2(xi[i][0], xj[j][0]);
+                            acc2[i * 8 + j] = __ffma2_rn(d, d, acc2[i * 8 + j]);
+                        }
+                }
+                float acc[WRO::kPadded];
+#pragma unroll
+                for (int s = 0; s < 64; ++s) acc[s] = acc2[s].x + acc2[s].y;
+                WRO::run(acc, s_tmp[warp], lane);
+                __syncwarp();
+                for (int l = lane; l < 64; l += 32) table[pair_slot<M>(rI + (l >> 3), rJ + (l & 7))] = s_tmp[warp][l];
+                __syncwarp();
+            }
+        }
+        // pass 2 reads every chunk: make sure this thread has observed all of them
+        while (waited < nchunks - 1) mbar_wait(&s_bar[++waited], 0);
+    }
+    __syncthreads();
+
+    // ---- sum over column splits and over the cluster (fixed order).  Cross-CTA: every CTA folds its splits into
+    //      table 0, then PULLS its peers' tables through distributed shared memory — no staging buffer. ----
+    if (cluster_size > 1) {
+        for (int s = tid; s < P; s += blockDim.x) {
+            float t = s_warp[s];
+            for (int k = 1; k < nsplit; ++k) t += s_warp[k * P + s];
+            s_warp[s] = t;
+        }
+        cluster_wait_acquire();     // phase 0: every CTA of the cluster is running
+        cluster_arrive_release();   // phase 1: my table 0 is complete
+        cluster_wait_acquire();
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    // one work item per (i, j >= i): j == i is the confinement distance of draw i
+    for (int idx = tid; idx < M * M; idx += blockDim.x) {
+        const int i = idx / M, j = idx - i * M;
+        if (j < i) continue;
+        const int s = (j == i) ? i : pair_slot<M>(i, j);
+        float total = 0.f;
+        if (cluster_size > 1) {
+            for (int r = 0; r < cluster_size; ++r) total += cluster.map_shared_rank(s_warp, r)[s];
+        } else {
+            for (int k = 0; k < nsplit; ++k) total += s_warp[k * P + s];
+        }
+        float val, der;
+        pow_value_deriv(total, p.pw, val, der);
+        s_val[s] = val;
+        if (j == i) {
+            s_A[i] = pre_conf * der;
+            s_K[idx] = 0.f;
+        } else {
+            s_K[idx] = pre_pair * der;
+        }
+        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
+    }
+    if (cluster_size > 1) cluster_arrive_release();  // phase 2: I no longer read my peers' tables
+    __syncthreads();
+
+    if (control) {
+        if (cluster_size > 1) cluster_wait_acquire();  // nobody's shared memory goes away while a peer may read it
+        if (rank == 0) {
+            float c = 0.f, it = 0.f;
+            for (int s = lane; s < P; s += 32) {
+                const float v = s_val[s];
+                if (s < M) c += v; else it += v;
+            }
+            c = warp_sum(c);
+            it = 2.0f * warp_sum(it);
+            finish_row(p, b, c, it, W, lane);
+        }
+        return;
+    }
+
+    // ---- pass 2: column owner ----
+    if (p.grad_xhat != nullptr && nq > 0) {
+        T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
+        const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
+        for (int q = tid; q < nq; q += nthr) {
+            float2 x[M][1], g[M][1], x0v[1];
+            lds_step<T, COLS>(x0row, q, x0v);
+#pragma unroll
+            for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+#pragma unroll
+            for (int i0 = 0; i0 < M; i0 += 4) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&s_A[i0]);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) g[i0 + u][0] = __fmul2_rn(make_float2(av[u], av[u]), sub2(x[i0 + u][0], x0v[0]));
+            }
+#pragma unroll
+            for (int i = 0; i < M - 1; ++i) {
+#pragma unroll
+                for (int j0 = ((i + 1) / 4) * 4; j0 < M; j0 += 4) {
+                    const float4 k4 = *reinterpret_cast<const float4*>(&s_K[i * M + j0]);
+                    const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + u;
+                        if (j <= i) continue;
+                        const float2 d = sub2(x[i][0], x[j][0]);
+                        g[i][0] = __ffma2_rn(make_float2(kv[u], kv[u]), d, g[i][0]);
+                        g[j][0] = __ffma2_rn(make_float2(-kv[u], -kv[u]), d, g[j][0]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+        }
+    }
+}
+
+}  // namespace dddm

@@ -1,0 +1,33 @@
+// energy_blk_launch.cuh — host-side launch of the blocked (m = 16, 32) packed-fp32 energy kernel.
+#pragma once
+
+#include "energy_blk.cuh"
+
+namespace dddm {
+
+template <typename T, int M>
+int launch_energy_blk_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
+    // two builds: register cap for 2 CTAs per SM (168) or uncapped for tiles that leave room for only one
+    const bool two = plan.smem_bytes <= 104 * 1024 && tuning().ctas != 1;
+    auto kernel = two ? energy_fused_blk_kernel<T, M, 2> : energy_fused_blk_kernel<T, M, 1>;
+    static size_t configured[2] = {0, 0};
+    size_t& conf = configured[two ? 1 : 0];
+    if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        conf = plan.smem_bytes;
+    }
+    return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
+                             p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);
+}
+
+template <typename T>
+int launch_energy_blk_any(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
+    switch (p.m) {
+        case 16: return launch_energy_blk_m<T, 16>(p, plan, stream);
+        case 32: return launch_energy_blk_m<T, 32>(p, plan, stream);
+        default: return DDDM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace dddm

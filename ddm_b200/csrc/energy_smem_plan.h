@@ -13,4 +13,8 @@ struct SmemPlan {
 SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16);
 template <typename T>
 int launch_energy_smem(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
+// blocked variant for m = 16, 32 (energy_blk.cuh)
+SmemPlan plan_blk(int m, int D, int elem_size, bool aligned16);
+template <typename T>
+int launch_energy_blk(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
 }  // namespace dddm

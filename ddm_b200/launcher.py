@@ -10,17 +10,18 @@ backward -> clip_grad_norm_ -> AdamW.step) and the same checkpoint payload (``:3
 Per step and per rank:
   K4  w-sum of the local t  ->  1-float NCCL all-reduce (async, overlaps the backbone forward)
   K2  x_t = alpha x0 + sigma eps written m-fold straight into the backbone input
-  backbone forward (PyTorch DDP; bf16 autocast optional)
+  backbone forward (PyTorch; bf16 shadow weights + bf16 activations by default, fp32 master weights)
   K1  fused energy-score loss forward + backward with the GLOBAL weight
-  backbone backward with DDP's bucketed gradient all-reduce (58 MB fp32) overlapped
-  fused AdamW; metrics stay on the device and are read back packed, once per log interval.
+  backbone backward into ONE flat gradient buffer -> one NCCL all-reduce(AVG) over NVLink/NVSwitch
+  device-side global-norm clip + fused AdamW; metrics stay on the device and are read back packed,
+  once per log interval.  The whole step replays as one CUDA graph (--cuda-graph).
 The batch is sharded by row (``--batch`` is per GPU, BASELINE config 4: 128/GPU); there is no
 other parallelism axis (14.5 M parameters, 64-token sequences).
 """
 from __future__ import annotations
 
 import argparse
-import contextlib
+import copy
 import json
 import os
 import time
@@ -65,6 +66,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--precision", choices=["fp32", "tf32", "bf16"], default="bf16",
                    help="backbone matmul precision (the loss kernels always accumulate in fp32)")
     p.add_argument("--log-every", type=int, default=20)
+    p.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
+                   help="capture the whole training step in one CUDA graph (default: on with --synthetic)")
+    p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
     return p
 
 
@@ -96,42 +100,126 @@ def init_distributed():
     return world, rank, dev
 
 
-def set_precision(precision: str):
-    torch.backends.cuda.matmul.allow_tf32 = precision != "fp32"
-    torch.backends.cudnn.allow_tf32 = precision != "fp32"
-    if precision == "bf16":
-        return lambda: torch.autocast("cuda", dtype=torch.bfloat16)
-    return contextlib.nullcontext
+def _flatten_(tensors, dtype) -> torch.Tensor:
+    """Re-home ``tensors`` (parameters) as views of ONE contiguous buffer and return it."""
+    flat = torch.empty(sum(t.numel() for t in tensors), dtype=dtype, device=tensors[0].device)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        flat[off:off + n].copy_(t.detach().reshape(-1))
+        t.data = flat[off:off + n].view_as(t)
+        off += n
+    return flat
 
 
 class Trainer:
-    """Model + optimizer + one data-parallel training step (used by main() and by bench.py)."""
+    """Model + optimizer + one data-parallel training step (used by main() and by bench.py).
 
-    def __init__(self, args, dev: torch.device, world: int):
+    Layout (no host synchronisation, no per-tensor launches, whole step in one CUDA graph):
+
+    * fp32 master parameters live in ONE flat buffer (AdamW state follows); with ``--precision bf16`` the
+      backbone computes on a bf16 shadow copy (also one flat buffer, refreshed by one cast kernel per step),
+      activations and gradients are bf16, the loss kernels accumulate in fp32;
+    * gradients are views of ONE flat buffer: data parallelism is a single NCCL all-reduce(AVG) of that buffer
+      after the backward (29 MB bf16 / 58 MB fp32 over NVLink/NVSwitch: ~0.1-0.3 ms against a >15 ms step, so
+      bucketed overlap buys nothing here), followed by global-norm clipping with the coefficient kept on
+      the device and fused AdamW;
+    * with ``--cuda-graph`` (default for --synthetic) the whole step — K4, the w-sum all-reduce, K2, backbone
+      forward, K1, backward, gradient all-reduce, clip, AdamW, shadow refresh — is captured once and replayed.
+    """
+
+    def __init__(self, args, dev: torch.device, world: int, module: torch.nn.Module | None = None, loss_fn=None):
+        """``module`` / ``loss_fn(model, x0) -> (loss, packed_metrics)`` default to the DiT and the DDDM step; the
+        CPU tests pass a small model and loss to exercise the flat-buffer / all-reduce / clip logic on gloo."""
         self.args, self.dev, self.world = args, dev, world
         torch.manual_seed(args.seed)  # identical initial weights on every rank
-        model = DDDMDiT(img_size=args.image_size, patch_size=args.patch_size, in_channels=6, out_channels=3,
-                        embed_dim=args.embed_dim, depth=args.depth, num_heads=args.heads,
-                        time_embed_dim=args.time_embed, mlp_ratio=args.mlp_ratio).to(dev)
-        self.module = model
+        if module is None:
+            module = DDDMDiT(img_size=args.image_size, patch_size=args.patch_size, in_channels=6, out_channels=3,
+                             embed_dim=args.embed_dim, depth=args.depth, num_heads=args.heads,
+                             time_embed_dim=args.time_embed, mlp_ratio=args.mlp_ratio)
+        self.module = module.to(dev)
+        self.module.train()
+        self.loss_fn = loss_fn or self._dddm_loss
+        self.bf16 = args.precision == "bf16"
+        torch.backends.cuda.matmul.allow_tf32 = args.precision != "fp32"
+        torch.backends.cudnn.allow_tf32 = args.precision != "fp32"
+        master = [p for p in self.module.parameters() if p.requires_grad]
+        self.flat_master = _flatten_(master, torch.float32)
         if world > 1:
-            model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], gradient_as_bucket_view=True)
-        self.model = model
-        self.opt = torch.optim.AdamW(self.module.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True)
-        self.autocast = set_precision(args.precision)
+            dist.broadcast(self.flat_master, src=0)  # identical start even if the caller seeded the ranks differently
+        self.flat_master_grad = torch.zeros_like(self.flat_master)
+        if self.bf16:
+            self.model = copy.deepcopy(self.module).to(torch.bfloat16)
+            shadow = [p for p in self.model.parameters() if p.requires_grad]
+            self.flat_shadow = _flatten_(shadow, torch.bfloat16)
+            self.flat_grad = torch.zeros_like(self.flat_shadow)
+            grad_owner = shadow
+        else:
+            self.model = self.module
+            self.flat_grad = self.flat_master_grad
+            grad_owner = master
+        off = 0
+        for p, q in zip(grad_owner, master):
+            n = p.numel()
+            p.grad = self.flat_grad[off:off + n].view_as(p)          # autograd accumulates in place
+            q.grad = self.flat_master_grad[off:off + n].view_as(q)   # what the optimizer reads
+            off += n
+        want_graph = getattr(args, "cuda_graph", None)
+        self.use_graph = dev.type == "cuda" and bool(getattr(args, "synthetic", False) if want_graph is None else want_graph)
+        self.opt = torch.optim.AdamW(master, lr=args.lr, weight_decay=args.weight_decay, fused=dev.type == "cuda",
+                                     capturable=self.use_graph)
+        self._graph = None
+        self._static_x0 = None
+        self._static_metrics = None
         torch.manual_seed(args.seed + 1 + (dist.get_rank() if world > 1 else 0))  # per-rank data / noise streams
 
-    def step(self, x0: torch.Tensor):
+    # -- one optimisation step, all on the current stream, no host synchronisation -------------------------
+    def _dddm_loss(self, model, x0):
         a = self.args
-        with self.autocast():
-            loss, metrics = distributional_training_step(self.model, x0, m=a.m, beta=a.beta, lam=a.lam,
-                                                         w_bias=a.w_bias, sync_metrics=False)
-        self.opt.zero_grad(set_to_none=True)
+        loss, metrics = distributional_training_step(model, x0, m=a.m, beta=a.beta, lam=a.lam, w_bias=a.w_bias,
+                                                     sync_metrics=False)
+        return loss, metrics.tensor
+
+    def _step_impl(self, x0: torch.Tensor) -> torch.Tensor:
+        a = self.args
+        self.flat_grad.zero_()
+        loss, packed = self.loss_fn(self.model, x0)
         loss.backward()
-        if a.grad_clip is not None and a.grad_clip > 0:
-            torch.nn.utils.clip_grad_norm_(self.module.parameters(), a.grad_clip)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        if self.bf16:
+            self.flat_master_grad.copy_(self.flat_grad)
+        if a.grad_clip is not None and a.grad_clip > 0:  # clip_grad_norm_ (train_cifar10_dit.py:167-168), device-side
+            coef = (a.grad_clip / (torch.linalg.vector_norm(self.flat_master_grad) + 1e-6)).clamp(max=1.0)
+            self.flat_master_grad.mul_(coef)
         self.opt.step()
-        return metrics
+        if self.bf16:
+            self.flat_shadow.copy_(self.flat_master)
+        return packed
+
+    def _capture(self, x0: torch.Tensor) -> None:
+        self._static_x0 = x0.clone()
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # warm-up: cuBLAS/cuDNN plans, optimizer state, NCCL communicators
+                self._step_impl(self._static_x0)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_metrics = self._step_impl(self._static_x0)
+
+    def step(self, x0: torch.Tensor):
+        from .training import DeferredMetrics
+
+        if not self.use_graph:
+            return DeferredMetrics(self._step_impl(x0))
+        if self._graph is None:
+            self._capture(x0)
+        self._static_x0.copy_(x0, non_blocking=True)
+        self._graph.replay()
+        return DeferredMetrics(self._static_metrics.clone())
 
     def synthetic_batch(self) -> torch.Tensor:
         a = self.args

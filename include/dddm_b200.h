@@ -160,7 +160,7 @@ int dddm_last_error(void);
 /* ------------------------------------------------------------------------------------------
  * Tuning / introspection (benchmarks and tests; never needed for correctness).
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
- *         3 = TMA-staged packed-fp32 kernel for m <= 8), "energy.cluster" (CTAs per row, 0 = auto),
+ *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto),
  *         "energy.threads" (threads per CTA of variant 3, 0 = auto), "energy.nv" (16-byte vectors per
  *         thread of variant 1, 0 = auto), "energy.pdl" (programmatic dependent launch, default 1), "energy.ctas" (experiment).
  * dddm_launch_count returns the number of kernels this library has launched in this process.

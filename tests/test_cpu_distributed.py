@@ -89,3 +89,61 @@ def test_launcher_flags_and_yaml_overlay(tmp_path):
     a = p.parse_args(["--config", str(cfg)])
     with pytest.raises(ValueError, match="Unknown config key"):
         launcher.apply_yaml(p, a)
+
+
+def _tiny_loss(model, x):
+    y = model(x)
+    loss = (y * y).mean() + 0.1 * y.abs().mean()
+    return loss, torch.stack([loss.detach(), loss.detach(), loss.detach(), loss.detach()])
+
+
+def _tiny_model():
+    return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
+
+
+def _trainer_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ddm_b200 import launcher
+
+        args = launcher.build_parser().parse_args(["--precision", "fp32", "--grad-clip", "0.05", "--lr", "1e-2"])
+        torch.manual_seed(0 if rank == 0 else 1234)  # only rank 0's initial weights may matter (broadcast at init)
+        tr = launcher.Trainer(args, torch.device("cpu"), world, module=_tiny_model(), loss_fn=_tiny_loss)
+        assert not tr.use_graph
+        gen = torch.Generator().manual_seed(1)
+        data = torch.randn(4, 8, 6, generator=gen)  # 4 steps of a global batch of 8
+        per = 8 // world
+        for step in range(4):
+            tr.step(data[step, rank * per:(rank + 1) * per])
+        # parameters are views of one flat buffer and identical on every rank
+        flat = tr.flat_master.clone()
+        other = flat.clone()
+        dist.all_reduce(other, op=dist.ReduceOp.SUM)
+        assert torch.allclose(other, world * flat, rtol=0, atol=1e-7)
+        assert all(p.data_ptr() >= tr.flat_master.data_ptr() for p in tr.module.parameters())
+        if rank == 0:
+            torch.save(flat, os.path.join(out_dir, "flat.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_flat_allreduce_clip_matches_single_process(tmp_path):
+    """Flat-buffer all-reduce(AVG) + device-side global-norm clip + AdamW over 2 ranks == the reference recipe
+    (zero_grad -> backward -> clip_grad_norm_ -> AdamW.step, train_cifar10_dit.py:152-169) on the global batch."""
+    world = 2
+    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    flat = torch.load(tmp_path / "flat.pt")
+    torch.manual_seed(0)  # Trainer seeds the initial weights with args.seed = 0
+    model = _tiny_model()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.01)
+    gen = torch.Generator().manual_seed(1)
+    data = torch.randn(4, 8, 6, generator=gen)
+    for step in range(4):
+        loss, _ = _tiny_loss(model, data[step])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
+        opt.step()
+    ref = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    assert torch.allclose(flat, ref, rtol=1e-5, atol=1e-7), float((flat - ref).abs().max())

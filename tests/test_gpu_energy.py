@@ -207,9 +207,39 @@ def test_kernel_variants_agree(dev):
             out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
             assert _rel(g, grad) <= FP32_REL
     finally:
-        for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl", "energy.threads"):
+        for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.threads"):
             _cabi.set_tuning(k, 0)
+        _cabi.set_tuning("energy.pdl", 1)
     assert len(seen) >= 12, seen
+
+
+@pytest.mark.parametrize("m", [16, 32])
+def test_blocked_kernel_plans_agree(dev, m):
+    """m = 16 / 32: the blocked packed-fp32 kernel (variant 4) under every cluster size and thread count, and the
+    generic chunked tile kernel (variant 2), against the oracle — fp32 and bf16, early and late regime, all betas."""
+    from ddm_b200 import _cabi
+
+    seen = set()
+    try:
+        for D, B in ((3072, 6), (1024, 5), (12288, 3), (64, 7)):
+            for regime, beta in (("late", 0.1), ("early", 1.0), ("late", 2.0)):
+                xh, x0 = _synthetic(B, m, D, regime, seed=m + D)
+                for variant, cluster, threads in ((4, 0, 0), (4, 1, 0), (4, 2, 64), (4, 4, 0), (4, 8, 32), (2, 0, 0)):
+                    _cabi.set_tuning("energy.variant", variant)
+                    _cabi.set_tuning("energy.cluster", cluster)
+                    _cabi.set_tuning("energy.threads", threads)
+                    try:
+                        _check_case(xh.numpy(), x0.numpy(), beta, dev)
+                        if beta == 0.1:
+                            _check_case(xh.numpy(), x0.numpy(), beta, dev, dtype=torch.bfloat16, rel=BF16_REL)
+                    except _cabi.DDDMError as e:
+                        assert e.status == -4, e  # plan does not cover the shape (tile too large for one CTA)
+                        continue
+                    seen.add(_cabi.describe_energy(B, m, D))
+    finally:
+        for k in ("energy.cluster", "energy.variant", "energy.threads"):
+            _cabi.set_tuning(k, 0)
+    assert sum(d.startswith("blk<") for d in seen) >= 8 and any(d.startswith("tile<") for d in seen), seen
 
 
 def test_deterministic_and_workspace_reuse(dev):
