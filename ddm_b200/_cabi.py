@@ -49,6 +49,10 @@ SIGNATURES = {
                                                  c_long, c_void_p]),
     "dddm_forward_marginal_expand_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                                   c_long, c_void_p]),
+    "dddm_forward_marginal_concat_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dddm_forward_marginal_concat_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                                  c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dddm_sigmoid_weight_sum_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "dddm_bridge_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
                                      c_void_p, c_void_p, c_long, c_long, c_void_p]),

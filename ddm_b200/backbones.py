@@ -146,16 +146,20 @@ class DDDMDiT(nn.Module):
             raise ValueError("Expecting image tensors with shape [B, C, H, W]")
         return self.forward_cat(torch.cat((xt, xi), dim=1), t)
 
-    def forward_cat(self, x6, t):
+    def forward_cat(self, x6, t, tokens: bool = False):
         """Same as ``forward`` with the channel concat cat(x_t, xi) already formed ([B, 6, H, W]); the
-        training step's K2 kernel writes that tensor directly."""
+        training step's K2c kernel writes that tensor directly.  ``tokens=True`` returns
+        PatchUnembed's projection ``[B, (H/p)(W/p), C*p*p]`` without the unpatchify permute/copy: the energy
+        score only needs x0 in the same order (K2c provides it)."""
         wdtype = self.patch_embed.proj.weight.dtype
-        tokens = self.patch_embed.proj(x6.to(wdtype)).flatten(2).transpose(1, 2)
+        emb = self.patch_embed.proj(x6.to(wdtype)).flatten(2).transpose(1, 2)
         temb = self.time_mlp(_sinusoidal(t.reshape(-1).float(), self.time_embed_dim).to(wdtype))
-        h = tokens + temb[:, None, :] + self.pos_embed
+        h = emb + temb[:, None, :] + self.pos_embed
         for blk in self.blocks:
             h = blk(h)
         y = self.unembed.proj(self.norm(h))
+        if tokens:
+            return y
         g, p, c = self.grid, self.patch_size, self.out_channels
         y = y.view(-1, g, g, c, p, p).permute(0, 3, 1, 4, 2, 5)
         return y.reshape(-1, c, self.img_size, self.img_size)

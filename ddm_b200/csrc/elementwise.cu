@@ -77,6 +77,88 @@ static int forward_marginal_expand(const T* x0, const float* t, const T* eps, T*
     return (int)cudaGetLastError();
 }
 
+// ---- K2c -----------------------------------------------------------------------------------
+// Forward marginal written m-fold straight into the channel-concatenated backbone input
+//   x6[b*m+i] = cat(x_t[b], xi[b,i])   ([B*m, 2C, H, W]; dddm/model.py:236 builds it with torch.cat),
+// optionally down-converted to bf16 on the way out, plus (optional) x0 re-ordered into the patch-token
+// layout PatchUnembed produces (dddm/model.py:125-128) so that the loss can consume the backbone's tokens
+// without the unpatchify copy: the energy score is invariant to a common permutation of the D axis.
+// One thread owns 4 consecutive pixels of one image row (W % 4 == 0, patch % 4 == 0).
+template <typename TI, typename TO>
+__device__ __forceinline__ void store4(TO* dst, const float (&v)[4]) {
+    if constexpr (sizeof(TO) == 4) {
+        stg_stream16(dst, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+    } else {
+        stg_stream8(dst, make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+    }
+}
+template <typename TI>
+__device__ __forceinline__ void load4(const TI* src, float (&v)[4]) {
+    if constexpr (sizeof(TI) == 4) {
+        const uint4 r = ldg_stream16(src);
+        v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+    } else {
+        const uint2 r = *reinterpret_cast<const uint2*>(src);
+        v[0] = bf16lo(r.x); v[1] = bf16hi(r.x); v[2] = bf16lo(r.y); v[3] = bf16hi(r.y);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+forward_marginal_concat_kernel(const TI* __restrict__ x0, const float* __restrict__ t, const TI* __restrict__ eps,
+                               const TI* __restrict__ xi, TO* __restrict__ x6, TI* __restrict__ x0_tok, int m, int C, int H,
+                               int W, int patch) {
+    const long D = (long)C * H * W;
+    const long nquad = D / 4;
+    const int b = blockIdx.y;
+    const float tb = t[b];
+    const float ab = 1.0f - tb;
+    const TI* x0r = x0 + (long)b * D;
+    const TI* er = eps + (long)b * D;
+    for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nquad; v += (long)gridDim.x * blockDim.x) {
+        const long e = v * 4;
+        float a[4], n[4], o[4];
+        load4<TI>(x0r + e, a);
+        load4<TI>(er + e, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = __fadd_rn(__fmul_rn(ab, a[k]), __fmul_rn(tb, n[k]));  // no FMA: matches eager
+        for (int i = 0; i < m; ++i) {
+            TO* dst = x6 + ((long)b * m + i) * 2 * D;
+            store4<TI, TO>(dst + e, o);
+            float z[4];
+            load4<TI>(xi + ((long)b * m + i) * D + e, z);
+            store4<TI, TO>(dst + D + e, z);
+        }
+        if (x0_tok != nullptr) {
+            const int x = (int)(e % W), y = (int)((e / W) % H), c = (int)(e / ((long)W * H));
+            const int gx = x / patch, px = x - gx * patch, gy = y / patch, py = y - gy * patch;
+            const long tok = (((long)gy * (W / patch) + gx) * C + c) * patch * patch + (long)py * patch + px;
+            store4<TI, TI>(x0_tok + (long)b * D + tok, a);
+        }
+    }
+}
+
+template <typename TI, typename TO>
+static int forward_marginal_concat(const TI* x0, const float* t, const TI* eps, const TI* xi, TO* x6, TI* x0_tok, int B,
+                                   int m, int C, int H, int W, int patch, cudaStream_t stream) {
+    if (!x0 || !t || !eps || !xi || !x6) return DDDM_ERR_NULL_POINTER;
+    if (B < 0 || m < 1 || C < 1 || H < 1 || W < 1 || B > 65535) return DDDM_ERR_BAD_SHAPE;
+    if (W % 4 != 0) return DDDM_ERR_UNSUPPORTED;
+    if (x0_tok && (patch < 4 || patch % 4 != 0 || W % patch != 0 || H % patch != 0)) return DDDM_ERR_BAD_SHAPE;
+    if (!aligned16(x0) || !aligned16(eps) || !aligned16(xi) || !aligned16(x6) || (x0_tok && !aligned16(x0_tok)))
+        return DDDM_ERR_BAD_ALIGNMENT;
+    if (B == 0) return DDDM_OK;
+    const long nquad = (long)C * H * W / 4;
+    const int threads = nquad >= 256 ? 256 : (int)((nquad + 31) / 32 * 32);
+    long tiles = (nquad + threads - 1) / threads;
+    const long max_tiles = ((long)num_sms() * 8 + B - 1) / B;
+    if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
+    forward_marginal_concat_kernel<TI, TO><<<dim3((unsigned)tiles, (unsigned)B), threads, 0, stream>>>(
+        x0, t, eps, xi, x6, x0_tok, m, C, H, W, patch);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 // ---- K4 ------------------------------------------------------------------------------------
 __device__ __forceinline__ float logistic_weight(float t, float bias) {
     const float a = 1.0f - t;
@@ -241,6 +323,25 @@ int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const
     return forward_marginal_expand<__nv_bfloat16>((const __nv_bfloat16*)x0, t, (const __nv_bfloat16*)eps,
                                                   (__nv_bfloat16*)xt, (__nv_bfloat16*)xt_rep, B, m, D,
                                                   (cudaStream_t)stream);
+}
+
+int dddm_forward_marginal_concat_f32(const float* x0, const float* t, const float* eps, const float* xi, void* x6,
+                                     int out_dtype, float* x0_tok, int B, int m, int C, int H, int W, int patch,
+                                     dddm_stream_t stream) {
+    if (out_dtype == DDDM_DTYPE_F32)
+        return forward_marginal_concat<float, float>(x0, t, eps, xi, (float*)x6, x0_tok, B, m, C, H, W, patch,
+                                                     (cudaStream_t)stream);
+    if (out_dtype == DDDM_DTYPE_BF16)
+        return forward_marginal_concat<float, __nv_bfloat16>(x0, t, eps, xi, (__nv_bfloat16*)x6, x0_tok, B, m, C, H, W,
+                                                             patch, (cudaStream_t)stream);
+    return DDDM_ERR_BAD_ARGUMENT;
+}
+int dddm_forward_marginal_concat_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, const dddm_bf16* xi,
+                                      dddm_bf16* x6, dddm_bf16* x0_tok, int B, int m, int C, int H, int W, int patch,
+                                      dddm_stream_t stream) {
+    return forward_marginal_concat<__nv_bfloat16, __nv_bfloat16>(
+        (const __nv_bfloat16*)x0, t, (const __nv_bfloat16*)eps, (const __nv_bfloat16*)xi, (__nv_bfloat16*)x6,
+        (__nv_bfloat16*)x0_tok, B, m, C, H, W, patch, (cudaStream_t)stream);
 }
 
 int dddm_sigmoid_weight_sum_f32(const float* t, float bias, float* w, float* w_sum, int B, dddm_stream_t stream) {

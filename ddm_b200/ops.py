@@ -251,6 +251,48 @@ def _fm_backward(ctx, g_xt, g_rep):
 forward_marginal_expand.register_autograd(_fm_backward, setup_context=_fm_setup)
 
 
+@torch.library.custom_op("ddm_b200::forward_marginal_concat", mutates_args=())
+def forward_marginal_concat(x0: Tensor, t: Tensor, eps: Tensor, xi: Tensor, out_bf16: bool,
+                            patch: int) -> Tuple[Tensor, Tensor]:
+    """K2c: x0, eps [B,C,H,W]; xi [B,m,C,H,W]; t [B].  Returns (x6 [B*m, 2C, H, W] = cat(x_t m-fold, xi) in fp32 or
+    bf16, x0 in patch-token order [B, C*H*W] or an empty tensor when patch == 0).  Not differentiable (data and noise)."""
+    _require_cuda(x0, t, eps, xi)
+    sfx = _suffix(x0)
+    if x0.dim() != 4 or eps.shape != x0.shape or xi.dim() != 5 or xi.shape[0] != x0.shape[0] or xi.shape[2:] != x0.shape[1:]:
+        raise ValueError(f"expected x0/eps [B,C,H,W] and xi [B,m,C,H,W], got {tuple(x0.shape)}, {tuple(eps.shape)}, "
+                         f"{tuple(xi.shape)}")
+    if eps.dtype != x0.dtype or xi.dtype != x0.dtype:
+        raise TypeError("x0, eps and xi must have the same dtype")
+    x0, eps, xi = x0.contiguous(), eps.contiguous(), xi.contiguous()
+    t = t.reshape(-1).float().contiguous()
+    B, C, H, W = x0.shape
+    m = xi.shape[1]
+    if t.numel() != B:
+        raise ValueError("t must have one entry per row of x0")
+    out_dtype = torch.bfloat16 if (out_bf16 or x0.dtype == torch.bfloat16) else torch.float32
+    x6 = torch.empty((B * m, 2 * C, H, W), dtype=out_dtype, device=x0.device)
+    tok = torch.empty((B, C * H * W) if patch > 0 else (0,), dtype=x0.dtype, device=x0.device)
+    with torch.cuda.device(x0.device):
+        L = _cabi.lib()
+        if sfx == "f32":
+            _cabi.check(L.dddm_forward_marginal_concat_f32(_ptr(x0), _ptr(t), _ptr(eps), _ptr(xi), _ptr(x6),
+                                                           1 if out_dtype == torch.bfloat16 else 0,
+                                                           _ptr(tok) if patch > 0 else None, B, m, C, H, W, patch, _stream(x0)))
+        else:
+            _cabi.check(L.dddm_forward_marginal_concat_bf16(_ptr(x0), _ptr(t), _ptr(eps), _ptr(xi), _ptr(x6),
+                                                            _ptr(tok) if patch > 0 else None, B, m, C, H, W, patch,
+                                                            _stream(x0)))
+    return x6, tok
+
+
+@forward_marginal_concat.register_fake
+def _(x0, t, eps, xi, out_bf16, patch):
+    B, C, H, W = x0.shape
+    dt = torch.bfloat16 if (out_bf16 or x0.dtype == torch.bfloat16) else torch.float32
+    return (x0.new_empty((B * xi.shape[1], 2 * C, H, W), dtype=dt),
+            x0.new_empty((B, C * H * W) if patch > 0 else (0,)))
+
+
 # --------------------------------------------------------------------------------------------
 # K4: logistic weight and its batch sum  (dddm/losses.py:28-35, dddm/training.py:84)
 # --------------------------------------------------------------------------------------------

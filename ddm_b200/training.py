@@ -77,6 +77,7 @@ def distributional_training_step(
     global_weight: Optional[bool] = None,
     group=None,
     sync_metrics: bool = True,
+    fused_io: Optional[bool] = None,
 ):
     """Generalized energy training loss (paper eqs. 12-14) — reference ``dddm/training.py:32-93``.
 
@@ -90,7 +91,11 @@ def distributional_training_step(
       the GLOBAL batch — one float all-reduce of sum_b w(t_b) issued before the backbone forward —
       so that a batch-sharded run equals the single-process global batch (the
       reference's loss is a product of two batch means).  Defaults to on when world_size > 1;
-    * ``sync_metrics=False`` returns a :class:`DeferredMetrics` (no host synchronisation in the step).
+    * ``sync_metrics=False`` returns a :class:`DeferredMetrics` (no host synchronisation in the step);
+    * ``fused_io`` (default: on when the model offers ``forward_cat``/``patch_size``, i.e. ``ddm_b200.backbones
+      .DDDMDiT``, and ``x0`` is an image batch): K2c writes cat(x_t, xi) m-fold directly in the backbone's compute
+      dtype and hands x0 over in patch-token order, and K1 reads the backbone's tokens without the unpatchify copy
+      (SURVEY.md §8f-2).  Same loss (the score is invariant to a common permutation of D), same RNG order.
 
     Kernels: K4 (weight sum) -> K2 (marginal + m-fold expansion, written straight into the
     backbone's input) -> backbone (PyTorch) -> K1 (fused loss forward + backward).
@@ -119,12 +124,22 @@ def distributional_training_step(
         work = dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=group, async_op=True)
     weight_scale = 1.0 / (batch * (world if use_global else 1))
 
-    _, xt_rep = ops.forward_marginal_expand(x0, t, eps, m, False)
-    xi_flat = xi.reshape(batch * m, *x0.shape[1:])
     t_rep = t.repeat_interleave(m)
-
-    x0hat = model(xt_rep, t_rep, xi_flat)
-    x0hat = x0hat.view(batch, m, *x0.shape[1:])
+    patch = int(getattr(model, "patch_size", 0) or 0)
+    can_fuse = (hasattr(model, "forward_cat") and x0.dim() == 4 and patch >= 4 and patch % 4 == 0 and
+                x0.shape[-1] % patch == 0 and x0.shape[-2] % patch == 0 and not x0.requires_grad)
+    if fused_io and not can_fuse:
+        raise ValueError("fused_io=True needs a backbone with forward_cat/patch_size and an image batch x0 [B,C,H,W]")
+    x0_flat = None
+    if can_fuse and fused_io is not False:
+        wdtype = next(model.parameters()).dtype
+        x6, x0_flat = ops.forward_marginal_concat(x0, t, eps, xi, wdtype == torch.bfloat16, patch)
+        x0hat = model.forward_cat(x6, t_rep, tokens=True).reshape(batch, m, -1)  # patch-token order, no unpatchify
+    else:
+        _, xt_rep = ops.forward_marginal_expand(x0, t, eps, m, False)
+        xi_flat = xi.reshape(batch * m, *x0.shape[1:])
+        x0hat = model(xt_rep, t_rep, xi_flat)
+        x0hat = x0hat.view(batch, m, *x0.shape[1:])
 
     if work is not None:
         work.wait()
@@ -138,7 +153,8 @@ def distributional_training_step(
         loss = weight * (conf - (lam / (2.0 * (m - 1))) * inter)
         packed = torch.stack([loss.detach().float(), conf.detach().float(), inter.detach().float(), weight.float()])
     else:
-        packed, _ = ops.energy_fused(x0hat.reshape(batch, m, -1).to(dtype), x0.reshape(batch, -1), w_sum,
+        packed, _ = ops.energy_fused(x0hat.reshape(batch, m, -1).to(dtype),
+                                     x0_flat if x0_flat is not None else x0.reshape(batch, -1), w_sum,
                                      weight_scale, float(beta), float(lam), want_grad)
         loss = packed[0].to(dtype)
         packed = packed.detach()

@@ -114,6 +114,25 @@ int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const
                                       dddm_bf16* xt_rep, int B, int m, long D, dddm_stream_t stream);
 
 /*
+ * K2c — the same marginal written m-fold straight into the backbone's channel-concatenated input
+ * (dddm/model.py:236 `torch.cat([xt, xi], dim=1)`, after the expansion of dddm/training.py:70-73):
+ *   x6[b*m+i, 0:C] = (1 - t[b]) * x0[b] + t[b] * eps[b];   x6[b*m+i, C:2C] = xi[b, i]      ([B*m, 2C, H, W])
+ * x6 is written in out_dtype (DDDM_DTYPE_F32 / DDDM_DTYPE_BF16: the down-conversion of a bf16 backbone's input
+ * is fused in).  x0_tok (nullable) receives x0 re-ordered into the patch-token layout of PatchUnembed
+ * (dddm/model.py:125-128: [B, (H/p)(W/p), C*p*p]) so the loss can read the backbone's tokens without the
+ * unpatchify copy — the energy score is invariant to a common permutation of the D axis.
+ * Needs W % 4 == 0 (and p % 4 == 0 when x0_tok is requested) and 16-byte aligned pointers.
+ */
+#define DDDM_DTYPE_F32 0
+#define DDDM_DTYPE_BF16 1
+int dddm_forward_marginal_concat_f32(const float* x0, const float* t, const float* eps, const float* xi, void* x6,
+                                     int out_dtype, float* x0_tok, int B, int m, int C, int H, int W, int patch,
+                                     dddm_stream_t stream);
+int dddm_forward_marginal_concat_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, const dddm_bf16* xi,
+                                      dddm_bf16* x6, dddm_bf16* x0_tok, int B, int m, int C, int H, int W, int patch,
+                                      dddm_stream_t stream);
+
+/*
  * K4 — sigmoid_weight (dddm/losses.py:28-35): w[b] = sigmoid(log((1-t)^2/(t^2+1e-12) + 1e-12) - bias);
  * w (nullable) receives the per-row weights, w_sum (nullable) their sum over B in a fixed order
  * (the caller all-reduces it across ranks and passes 1/(ranks*B) as weight_scale to K1).

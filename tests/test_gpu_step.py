@@ -287,3 +287,66 @@ def test_sharded_ranks_equal_global_batch(dev):
     got = torch.cat(grads, dim=0)
     assert float((got - grad_g).abs().max()) <= 2e-6 * float(grad_g.abs().max())
     assert abs(float(torch.stack(losses).mean()) - float(out_g[0])) <= 2e-6 * abs(float(out_g[0]))
+
+
+def _patchify(x, p):
+    """[B,C,H,W] -> [B, (H/p)(W/p), C*p*p]: the layout of PatchUnembed's projection (dddm/model.py:125-128)."""
+    B, C, H, W = x.shape
+    return x.view(B, C, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B, (H // p) * (W // p), C * p * p)
+
+
+def test_forward_marginal_concat_bit_exact(dev):
+    """K2c == cat(forward_marginal_sample(...) expanded m-fold, xi) bit for bit (fp32), RN-rounded for a bf16
+    backbone, and x0 in patch-token order (dddm/training.py:66-73, dddm/model.py:236)."""
+    from ddm_b200 import ops
+    from oracle import torch_port
+
+    gen = torch.Generator().manual_seed(3)
+    for B, m, C, H, W, p in ((5, 3, 3, 32, 32, 4), (2, 8, 3, 16, 24, 8), (3, 2, 1, 8, 8, 4)):
+        x0 = (torch.rand(B, C, H, W, generator=gen) * 2 - 1)
+        eps, xi, t = torch.randn(B, C, H, W, generator=gen), torch.randn(B, m, C, H, W, generator=gen), torch.rand(B, generator=gen)
+        xt = torch_port.forward_marginal(x0, t, eps)  # CPU eager fp32 = the reference's arithmetic
+        want = torch.cat([xt[:, None].expand(B, m, C, H, W).reshape(B * m, C, H, W), xi.reshape(B * m, C, H, W)], dim=1)
+        x6, tok = ops.forward_marginal_concat(x0.to(dev), t.to(dev), eps.to(dev), xi.to(dev), False, p)
+        assert x6.dtype == torch.float32 and torch.equal(x6.cpu(), want)
+        assert torch.equal(tok.cpu().view(B, -1), _patchify(x0, p).reshape(B, -1))
+        x6b, tok0 = ops.forward_marginal_concat(x0.to(dev), t.to(dev), eps.to(dev), xi.to(dev), True, 0)
+        assert x6b.dtype == torch.bfloat16 and tok0.numel() == 0 and torch.equal(x6b.cpu(), want.bfloat16())
+        xb = [v.bfloat16() for v in (x0, eps, xi)]
+        x6c, tokc = ops.forward_marginal_concat(xb[0].to(dev), t.to(dev), xb[1].to(dev), xb[2].to(dev), False, p)
+        xtb = ((1 - t).view(B, 1, 1, 1) * xb[0].float() + t.view(B, 1, 1, 1) * xb[1].float())
+        wantb = torch.cat([xtb[:, None].expand(B, m, C, H, W).reshape(B * m, C, H, W),
+                           xb[2].float().reshape(B * m, C, H, W)], dim=1).bfloat16()
+        assert x6c.dtype == torch.bfloat16 and torch.equal(x6c.cpu(), wantb)
+        assert torch.equal(tokc.cpu().view(B, -1), _patchify(xb[0], p).reshape(B, -1))
+    with pytest.raises(ValueError):
+        ops.forward_marginal_concat(x0.to(dev), t.to(dev), eps.to(dev), xi[:, :, :, :4].to(dev), False, 4)
+
+
+def test_fused_io_step_equals_generic_step(dev):
+    """The DiT fast path (K2c -> forward_cat(tokens=True) -> K1 on patch-token order) gives the same loss, metrics
+    and parameter gradients as the generic path (K2 -> model(x_t, t, xi) -> K1), in fp32 and with a bf16 backbone."""
+    import ddm_b200
+    from ddm_b200.backbones import DDDMDiT
+
+    torch.manual_seed(0)
+    B, m = 6, 4
+    x0 = (torch.rand(B, 3, 32, 32) * 2 - 1).to(dev)
+    t, eps, xi = torch.rand(B).to(dev), torch.randn(B, 3, 32, 32).to(dev), torch.randn(B, m, 3, 32, 32).to(dev)
+    for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 3e-2)):
+        torch.manual_seed(1)
+        model = DDDMDiT(depth=2, embed_dim=96, num_heads=3).to(dev).to(dtype)
+        torch.nn.init.normal_(model.unembed.proj.weight, std=0.05)
+        res = {}
+        for fused in (True, False):
+            model.zero_grad(set_to_none=True)
+            loss, met = ddm_b200.distributional_training_step(model, x0, m=m, beta=0.1, lam=1.0, w_bias=0.0, t=t, eps=eps,
+                                                              xi=xi, fused_io=fused)
+            loss.backward()
+            res[fused] = (float(loss), met, torch.cat([p.grad.float().reshape(-1) for p in model.parameters()]))
+        (la, ma, ga), (lb, mb, gb) = res[True], res[False]
+        assert abs(la - lb) <= tol * abs(lb), (dtype, la, lb)
+        assert all(abs(ma[k] - mb[k]) <= tol * max(abs(mb[k]), 1e-6) for k in ma)
+        assert float((ga - gb).abs().max()) <= tol * float(gb.abs().max()), (dtype, float((ga - gb).abs().max()))
+    with pytest.raises(ValueError):
+        ddm_b200.distributional_training_step(MixModel().to(dev), x0, m=m, beta=0.1, lam=1.0, w_bias=0.0, fused_io=True)
