@@ -104,6 +104,31 @@ def cpu_port_rate(seconds: float, dtype_name: str):
     return B / mean, n, torch.get_num_threads(), mean, best
 
 
+def gpu_eager_rate(dev, iters: int = 30):
+    """A second, tougher baseline: the reference's own eager PyTorch path (the port in
+    oracle/torch_port.py, same ops as dddm/losses.py + autograd) run on the SAME B200.  Reported, never shipped."""
+    import torch
+
+    from oracle import torch_port
+
+    xh, x0, t = make_inputs(0, torch.float32)
+    xh, x0, t = xh.to(dev), x0.to(dev), t.to(dev)
+    w = torch_port.sigmoid_weight(t, W_BIAS).mean()
+    for _ in range(3):
+        torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": B / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "kind": "port-on-gpu",
+            "sample": f"{iters} fwd+bwd passes of oracle/torch_port.py (eager PyTorch ops + autograd, as dddm/losses.py) on "
+                      f"the same B200, fp32, inputs resident"}
+
+
 def run_reference(args) -> None:
     """--impl reference: the reference's own CPU implementation of the path (oracle port: the
     reference is pure Python/PyTorch and /root/reference is absent on the GPU box)."""
@@ -370,8 +395,15 @@ def main() -> None:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = algo_bytes / (elapsed / K) / 1e9
 
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", f"k1_traffic_{args.dtype}.json")
+    if os.path.exists(tpath):  # dram bytes of ONE launch from the committed ncu --set full capture (tools/ncu_summary.py)
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+
     if rank == 0:
         cpu = None
+        eager = gpu_eager_rate(dev) if world == 1 and args.cpu_seconds > 0 else None
         if world == 1 and args.cpu_seconds > 0:
             rate, n, threads, mean, best = cpu_port_rate(args.cpu_seconds, args.dtype)
             cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
@@ -386,8 +418,9 @@ def main() -> None:
                        "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
                        "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 8x L2 "
                                     f"(every launch reads HBM-cold inputs)",
-                       "launch": (f"CUDA graphs; the independent steps are issued round-robin on {nstreams} streams "
-                                  f"(fork/join inside the graph) so consecutive minibatches overlap" if use_graph
+                       "launch": (f"CUDA graphs, programmatic dependent launch; the independent steps are issued round-robin "
+                                  f"on {nstreams} streams (fork/join inside the graph) so consecutive minibatches overlap"
+                                  if use_graph
                                   else "python launches, one stream"),
                        "single_stream_ms_per_step": serial_ms,
                        "single_stream_rows_per_s": B / (serial_ms * 1e-3),
@@ -395,9 +428,11 @@ def main() -> None:
                                        f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
                        "tuning": args.tune or "auto"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "frac_of_8TBs_nominal": achieved / 8000.0},
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
                     "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait"},

@@ -4,10 +4,10 @@
 // the (m+1) x slab tile with chunked 1-D TMA bulk copies, 128 compute threads, PDL, fence-free row
 // publication), but the m(m+1)/2 squared distances no longer fit a thread's registers, so the two
 // passes are organised differently:
-//   pass 1  "sweeps" over 8x8 blocks of the pair matrix: a thread walks its columns once per sweep with
-//           the block's 64 (off-diagonal block) or 2 x 36 (two diagonal blocks incl. the confinement
-//           column) accumulators in registers, differences and squares in packed fp32 (FADD2/FFMA2);
-//           each sweep ends in a butterfly warp reduction into the per-warp pair table;
+//   pass 1  "sweeps" over 8x8 blocks of the pair matrix: a warp walks a sweep's columns with the block's 64
+//           (off-diagonal block) or 2 x 28 (two diagonal blocks) accumulators in registers, differences and
+//           squares in packed fp32 (FADD2/FFMA2); each sweep ends in a butterfly warp reduction into the pair
+//           table.  The m confinement distances are accumulated by the control warp once its copies are issued;
 //   coeffs  f and f' for all P distances (all threads), K as a full m x m table in shared memory;
 //   pass 2  column owner: a thread keeps all m gradient rows of its 2 columns in registers (m float2),
 //           streams the coefficients from shared memory (LDS.128, uniform address = broadcast) and forms
@@ -46,13 +46,13 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     constexpr int COLS = kBlkCols;
     constexpr int U = Step<T, COLS>::kPerVec;
     constexpr int NB = M / 8;
-    using WRD = WarpReduce<72>;
+    using WRD = WarpReduce<56>;
     using WRO = WarpReduce<64>;
     __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
     __shared__ __align__(16) float s_K[M * M];   // K[i][j], j > i used
     __shared__ __align__(16) float s_A[M];       // confinement coefficients
     __shared__ float s_val[P];
-    __shared__ float s_tmp[kSmemMaxThreads / 32][72];
+    __shared__ float s_tmp[kSmemMaxThreads / 32][64];
     extern __shared__ __align__(128) unsigned char s_dyn[];
     // dynamic layout: tile [(M+1) x slab_vecs x 16] | s_warp [nsplit][P] (one pair table per column split)
     const int row_bytes = slab_vecs * 16;
@@ -95,6 +95,30 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     }
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
+    if (control) {
+        // the otherwise idle control warp owns the M confinement distances ||x_i - x0||^2 (slots 0..M-1 of table 0)
+        const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
+        float2 acc2[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc2[i] = make_float2(0.f, 0.f);
+        int waited = -1;
+        for (int q = lane; q < nq; q += 32) {
+            for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
+            float2 x0v[1];
+            lds_step<T, COLS>(x0row, q, x0v);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                float2 xv[1];
+                lds_step<T, COLS>(s_tile + (size_t)i * row_bytes, q, xv);
+                const float2 d = sub2(xv[0], x0v[0]);
+                acc2[i] = __ffma2_rn(d, d, acc2[i]);
+            }
+        }
+        float acc[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] = acc2[i].x + acc2[i].y;
+        WarpReduce<M>::run(acc, s_warp, lane);  // conf slot i == table-0 entry i
+    }
     const float nb = (float)p.B * (float)M;
     const float pre_conf = 2.0f * W / nb;
     const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
@@ -111,53 +135,39 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
             const int q_begin = (int)((long)nq * split / nsplit), q_end = (int)((long)nq * (split + 1) / nsplit);
             float* table = s_warp + split * P;
             if (sweep < NB / 2) {
-                // two diagonal blocks: 8 confinement + 28 pair accumulators each
+                // two diagonal blocks: 28 pair accumulators each
                 const int rA = 16 * sweep, rB = rA + 8;
-                float2 acc2[72];
+                float2 acc2[56];
 #pragma unroll
-                for (int s = 0; s < 72; ++s) acc2[s] = make_float2(0.f, 0.f);
+                for (int s = 0; s < 56; ++s) acc2[s] = make_float2(0.f, 0.f);
                 for (int q = q_begin + lane; q < q_end; q += 32) {
                     for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
-                    float2 x0v[1], xa[8][1], xb[8][1];
-                    lds_step<T, COLS>(x0row, q, x0v);
+                    float2 xa[8][1], xb[8][1];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         lds_step<T, COLS>(s_tile + (size_t)(rA + r) * row_bytes, q, xa[r]);
                         lds_step<T, COLS>(s_tile + (size_t)(rB + r) * row_bytes, q, xb[r]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 da = sub2(xa[i][0], x0v[0]);
-                        acc2[i] = __ffma2_rn(da, da, acc2[i]);
-                        const float2 db = sub2(xb[i][0], x0v[0]);
-                        acc2[36 + i] = __ffma2_rn(db, db, acc2[36 + i]);
-                    }
-#pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll
                         for (int j = i + 1; j < 8; ++j) {
                             const float2 da = sub2(xa[i][0], xa[j][0]);
-                            acc2[pair_slot<8>(i, j)] = __ffma2_rn(da, da, acc2[pair_slot<8>(i, j)]);
+                            acc2[pair_slot<8>(i, j) - 8] = __ffma2_rn(da, da, acc2[pair_slot<8>(i, j) - 8]);
                             const float2 db = sub2(xb[i][0], xb[j][0]);
-                            acc2[36 + pair_slot<8>(i, j)] = __ffma2_rn(db, db, acc2[36 + pair_slot<8>(i, j)]);
+                            acc2[28 + pair_slot<8>(i, j) - 8] = __ffma2_rn(db, db, acc2[28 + pair_slot<8>(i, j) - 8]);
                         }
                 }
                 float acc[WRD::kPadded];
 #pragma unroll
-                for (int s = 0; s < 72; ++s) acc[s] = acc2[s].x + acc2[s].y;
+                for (int s = 0; s < WRD::kPadded; ++s) acc[s] = (s < 56) ? acc2[s < 56 ? s : 0].x + acc2[s < 56 ? s : 0].y : 0.f;
                 WRD::run(acc, s_tmp[warp], lane);
                 __syncwarp();
-                for (int l = lane; l < 72; l += 32) {
-                    const int blk = l / 36, ll = l - 36 * blk, r0 = blk ? rB : rA;
-                    int slot;
-                    if (ll < 8) {
-                        slot = r0 + ll;
-                    } else {
-                        int i, j;
-                        unpair8(ll - 8, i, j);
-                        slot = pair_slot<M>(r0 + i, r0 + j);
-                    }
-                    table[slot] = s_tmp[warp][l];
+                for (int l = lane; l < 56; l += 32) {
+                    const int blk = l / 28, r0 = blk ? rB : rA;
+                    int i, j;
+                    unpair8(l - 28 * blk, i, j);
+                    table[pair_slot<M>(r0 + i, r0 + j)] = s_tmp[warp][l];
                 }
                 __syncwarp();
             } else {
@@ -173,19 +183,19 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 for (int s = 0; s < 64; ++s) acc2[s] = make_float2(0.f, 0.f);
                 for (int q = q_begin + lane; q < q_end; q += 32) {
                     for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
-                    float2 xi[8][1], xj[8][1];
+                    float2 xi[8][1];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        lds_step<T, COLS>(s_tile + (size_t)(rI + r) * row_bytes, q, xi[r]);
-                        lds_step<T, COLS>(s_tile + (size_t)(rJ + r) * row_bytes, q, xj[r]);
-                    }
+                    for (int r = 0; r < 8; ++r) lds_step<T, COLS>(s_tile + (size_t)(rI + r) * row_bytes, q, xi[r]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int j = 0; j < 8; ++j) {  // rows of block J are streamed one at a time (register budget)
+                        float2 xj[1];
+                        lds_step<T, COLS>(s_tile + (size_t)(rJ + j) * row_bytes, q, xj);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float2 d = sub2(xi[i][0], xj[j][0]);
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 d = sub2(xi[i][0], xj[0]);
                             acc2[i * 8 + j] = __ffma2_rn(d, d, acc2[i * 8 + j]);
                         }
+                    }
                 }
                 float acc[WRO::kPadded];
 #pragma unroll
