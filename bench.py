@@ -165,10 +165,53 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_aux(args, dev, world) -> dict:
+    """Auxiliary, outside the timed region: BASELINE configs 4 (DP DiT training img/s) and 5 (Algorithm-2 sampler)."""
+    import torch
+    import torch.distributed as dist
+
+    aux = {}
+    if args.dit_steps > 0:
+        from ddm_b200 import launcher
+
+        targs = launcher.build_parser().parse_args(["--synthetic", "--precision", args.dit_precision])
+        aux["dit_train"] = launcher.measure_throughput(targs, dev, world, steps=args.dit_steps, warmup=3)
+        aux["dit_train"]["config"] = ("DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
+                                      "data-parallel (one flat-gradient NCCL all-reduce), loss kernels K4+K2c+K1")
+    if args.sampler_samples > 0:
+        from ddm_b200.backbones import DDDMDiT
+        from ddm_b200.sampling import sample_dddm
+
+        per = max(1, args.sampler_samples // world)
+        net = DDDMDiT().to(dev)
+        if args.dit_precision == "bf16":
+            net = net.to(torch.bfloat16)  # bf16 weights and activations; x_t, the noise and the K3 update stay fp32
+        res = {}
+        if True:
+            for nsteps in (20, 100):
+                sample_dddm(net, per, steps=2, device=str(dev), data_shape=(3, 32, 32))
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                sample_dddm(net, per, steps=nsteps, device=str(dev), data_shape=(3, 32, 32))
+                a1.record()
+                a1.synchronize()
+                dt = a0.elapsed_time(a1) * 1e-3
+                if world > 1:
+                    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt)
+                res[f"steps{nsteps}"] = {"samples_per_s": per * world / dt, "seconds": dt}
+        aux["sampler"] = {"n_samples": per * world, "per_gpu": per, "model": "DDDMDiT(default)", **res}
+    return aux
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
@@ -183,6 +226,7 @@ def main() -> None:
                     help="auxiliary: DP DiT training steps to time for the img/s figure (0 = skip)")
     ap.add_argument("--dit-precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--sampler-samples", type=int, default=1024, help="auxiliary: Algorithm-2 samples (0 = skip)")
+    ap.add_argument("--aux-timeout", type=float, default=240.0, help="seconds the auxiliary measurements may take")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -353,41 +397,6 @@ def main() -> None:
     h2d = (B * M * D + B * D) * esz + B * 4
     d2h = B * M * D * esz + 16
 
-    # ---- auxiliary (outside the timed region above): BASELINE configs 4 and 5 on the same GPUs ----
-    aux = {}
-    if args.dit_steps > 0:
-        from ddm_b200 import launcher
-
-        targs = launcher.build_parser().parse_args(["--synthetic", "--precision", args.dit_precision])
-        aux["dit_train"] = launcher.measure_throughput(targs, dev, world, steps=args.dit_steps, warmup=3)
-        aux["dit_train"]["config"] = ("DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
-                                      "data-parallel (DDP over NCCL), loss kernels K4+K2+K1 fused path")
-    if args.sampler_samples > 0:
-        from ddm_b200.backbones import DDDMDiT
-        from ddm_b200.sampling import sample_dddm
-
-        per = max(1, args.sampler_samples // world)
-        net = DDDMDiT().to(dev)
-        res = {}
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.dit_precision == "bf16"):
-            for nsteps in (20, 100):
-                sample_dddm(net, per, steps=2, device=str(dev), data_shape=(3, 32, 32))
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                sample_dddm(net, per, steps=nsteps, device=str(dev), data_shape=(3, 32, 32))
-                a1.record()
-                a1.synchronize()
-                dt = a0.elapsed_time(a1) * 1e-3
-                if world > 1:
-                    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    dt = float(tt)
-                res[f"steps{nsteps}"] = {"samples_per_s": per * world / dt, "seconds": dt}
-        aux["sampler"] = {"n_samples": per * world, "per_gpu": per, "model": "DDDMDiT(default)", **res}
-
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
@@ -401,47 +410,67 @@ def main() -> None:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
 
-    if rank == 0:
-        cpu = None
-        eager = gpu_eager_rate(dev) if world == 1 and args.cpu_seconds > 0 else None
-        if world == 1 and args.cpu_seconds > 0:
-            rate, n, threads, mean, best = cpu_port_rate(args.cpu_seconds, args.dtype)
-            cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
-                   "sample": f"{n} full fwd+bwd passes over the same B={B},m={M},D={D} fp32 batch with oracle/torch_port.py "
-                             f"(eager PyTorch + autograd, the reference's CPU path), mean {mean * 1e3:.1f} ms, best "
-                             f"{best * 1e3:.1f} ms, os.cpu_count()={os.cpu_count()}"}
-        line = {
-            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": workload_name(args.dtype), "rows_per_gpu": B, "global_rows": B * world,
-                       "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
-                       "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 8x L2 "
-                                    f"(every launch reads HBM-cold inputs)",
-                       "launch": (f"CUDA graphs, programmatic dependent launch; the independent steps are issued round-robin "
-                                  f"on {nstreams} streams (fork/join inside the graph) so consecutive minibatches overlap"
-                                  if use_graph
-                                  else "python launches, one stream"),
-                       "single_stream_ms_per_step": serial_ms,
-                       "single_stream_rows_per_s": B / (serial_ms * 1e-3),
-                       "timed_region": f"median of {len(times)} repetitions of exactly {K} steps (CUDA events on the "
-                                       f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
-                       "tuning": args.tune or "auto"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                         "frac_of_8TBs_nominal": achieved / 8000.0},
-            "cpu_baseline": cpu,
-            "gpu_eager_baseline": eager,
-            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-                    "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait"},
-            "gpu_launches": K * len(times) // len(times),
-            "clocks": sampler.summary(),
-            "aux": aux,
-            "all_region_ms_per_step": [1e3 * x / K for x in times],
-        }
-        print(json.dumps(line), flush=True)
+    cpu = eager = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        eager = gpu_eager_rate(dev)
+        rate, n, threads, mean, best = cpu_port_rate(args.cpu_seconds, args.dtype)
+        cpu = {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{n} full fwd+bwd passes over the same B={B},m={M},D={D} fp32 batch with oracle/torch_port.py "
+                         f"(eager PyTorch + autograd, the reference's CPU path), mean {mean * 1e3:.1f} ms, best "
+                         f"{best * 1e3:.1f} ms, os.cpu_count()={os.cpu_count()}"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args.dtype), "rows_per_gpu": B, "global_rows": B * world,
+                   "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
+                   "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 8x L2 "
+                                f"(every launch reads HBM-cold inputs)",
+                   "launch": (f"CUDA graphs, programmatic dependent launch; the independent steps are issued round-robin "
+                              f"on {nstreams} streams (fork/join inside the graph) so consecutive minibatches overlap"
+                              if use_graph else "python launches, one stream"),
+                   "single_stream_ms_per_step": serial_ms,
+                   "single_stream_rows_per_s": B / (serial_ms * 1e-3),
+                   "timed_region": f"median of {len(times)} repetitions of exactly {K} steps (CUDA events on the "
+                                   f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
+                   "tuning": args.tune or "auto"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                     "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "single_stream_frac": algo_bytes / (serial_ms * 1e-3) / 1e9 / peak},
+        "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
+                "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait"},
+        "gpu_launches": K,
+        "clocks": sampler.summary(),
+        "all_region_ms_per_step": [1e3 * x / K for x in times],
+    }
+
+    # The auxiliary figures must never cost the headline line: a watchdog prints the line without them and ends
+    # every rank if they do not finish in time (e.g. a collective that never completes).
+    emitted = threading.Lock()
+
+    def emit(aux_value) -> None:
+        if emitted.acquire(blocking=False) and rank == 0:
+            line["aux"] = aux_value
+            print(json.dumps(line), flush=True)
+
+    def on_timeout() -> None:
+        emit({"error": f"auxiliary DiT/sampler measurements did not finish within {args.aux_timeout:.0f} s and were dropped"})
+        os._exit(0)
+
+    watchdog = threading.Timer(args.aux_timeout, on_timeout)
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        aux = run_aux(args, dev, world)
+    except Exception as exc:  # noqa: BLE001 - report, keep the headline
+        aux = {"error": f"{type(exc).__name__}: {exc}"}
+    watchdog.cancel()
+    emit(aux)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -124,8 +124,9 @@ class Trainer:
       after the backward (29 MB bf16 / 58 MB fp32 over NVLink/NVSwitch: ~0.1-0.3 ms against a >15 ms step, so
       bucketed overlap buys nothing here), followed by global-norm clipping with the coefficient kept on
       the device and fused AdamW;
-    * with ``--cuda-graph`` (default for --synthetic) the whole step — K4, the w-sum all-reduce, K2, backbone
-      forward, K1, backward, gradient all-reduce, clip, AdamW, shadow refresh — is captured once and replayed.
+    * with ``--cuda-graph`` (default for --synthetic) the step is captured once and replayed: on one GPU as ONE
+      graph (K4, K2c, backbone forward, K1, backward, clip, AdamW, shadow refresh); on several GPUs as two graphs
+      with the two NCCL all-reduces (the w-sum float, the flat gradient) issued eagerly between them.
     """
 
     def __init__(self, args, dev: torch.device, world: int, module: torch.nn.Module | None = None, loss_fn=None):
@@ -168,25 +169,29 @@ class Trainer:
         self.use_graph = dev.type == "cuda" and bool(getattr(args, "synthetic", False) if want_graph is None else want_graph)
         self.opt = torch.optim.AdamW(master, lr=args.lr, weight_decay=args.weight_decay, fused=dev.type == "cuda",
                                      capturable=self.use_graph)
-        self._graph = None
-        self._static_x0 = None
+        # NCCL is never captured: with several ranks the step is split into two graphs around the collectives
+        self.split_graph = self.use_graph and (world > 1 or os.environ.get("DDDM_SPLIT_GRAPH") == "1") and loss_fn is None
+        self._graph = self._graph_update = None
+        self._static_x0 = self._static_t = self._static_wsum = None
         self._static_metrics = None
         torch.manual_seed(args.seed + 1 + (dist.get_rank() if world > 1 else 0))  # per-rank data / noise streams
 
     # -- one optimisation step, all on the current stream, no host synchronisation -------------------------
-    def _dddm_loss(self, model, x0):
+    def _dddm_loss(self, model, x0, **kw):
         a = self.args
         loss, metrics = distributional_training_step(model, x0, m=a.m, beta=a.beta, lam=a.lam, w_bias=a.w_bias,
-                                                     sync_metrics=False)
+                                                     sync_metrics=False, **kw)
         return loss, metrics.tensor
 
-    def _step_impl(self, x0: torch.Tensor) -> torch.Tensor:
-        a = self.args
+    # -- the step in two device-side phases with the gradient all-reduce between them; no host synchronisation ----
+    def _fwd_bwd(self, x0: torch.Tensor, **kw) -> torch.Tensor:
         self.flat_grad.zero_()
-        loss, packed = self.loss_fn(self.model, x0)
+        loss, packed = self.loss_fn(self.model, x0, **kw)
         loss.backward()
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        return packed
+
+    def _update(self) -> None:
+        a = self.args
         if self.bf16:
             self.flat_master_grad.copy_(self.flat_grad)
         if a.grad_clip is not None and a.grad_clip > 0:  # clip_grad_norm_ (train_cifar10_dit.py:167-168), device-side
@@ -195,20 +200,56 @@ class Trainer:
         self.opt.step()
         if self.bf16:
             self.flat_shadow.copy_(self.flat_master)
+
+    def _step_impl(self, x0: torch.Tensor) -> torch.Tensor:
+        packed = self._fwd_bwd(x0)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        self._update()
+        return packed
+
+    # -- CUDA graphs.  One GPU: the whole step is ONE graph.  Several GPUs: NCCL stays outside the graphs (eager
+    #    collectives between replays are robust across NCCL/driver versions): [rand t, K4, all-reduce w-sum] ->
+    #    graph A (K2c, backbone forward, K1, backward) -> all-reduce(flat gradient) -> graph B (clip, AdamW, refresh).
+    def _weights(self, batch: int) -> None:
+        from . import ops
+
+        self._static_t.copy_(torch.rand(batch, device=self.dev, dtype=self._static_t.dtype))  # first draw of the step
+        _, w = ops.sigmoid_weight_sum(self._static_t, float(self.args.w_bias))
+        if self.world > 1:
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        self._static_wsum.copy_(w)
+
+    def _split_step_eager(self, x0: torch.Tensor) -> torch.Tensor:
+        self._weights(x0.shape[0])
+        packed = self._fwd_bwd(x0, t=self._static_t, weight_sum=self._static_wsum)
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        self._update()
         return packed
 
     def _capture(self, x0: torch.Tensor) -> None:
         self._static_x0 = x0.clone()
+        self._static_t = torch.zeros(x0.shape[0], device=self.dev, dtype=x0.dtype)
+        self._static_wsum = torch.zeros(1, device=self.dev)
+        eager = self._split_step_eager if self.split_graph else self._step_impl
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             for _ in range(3):  # warm-up: cuBLAS/cuDNN plans, optimizer state, NCCL communicators
-                self._step_impl(self._static_x0)
+                eager(self._static_x0)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self._graph = torch.cuda.CUDAGraph()
+        if not self.split_graph:
+            with torch.cuda.graph(self._graph):
+                self._static_metrics = self._step_impl(self._static_x0)
+            return
         with torch.cuda.graph(self._graph):
-            self._static_metrics = self._step_impl(self._static_x0)
+            self._static_metrics = self._fwd_bwd(self._static_x0, t=self._static_t, weight_sum=self._static_wsum)
+        self._graph_update = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_update):
+            self._update()
 
     def step(self, x0: torch.Tensor):
         from .training import DeferredMetrics
@@ -218,7 +259,14 @@ class Trainer:
         if self._graph is None:
             self._capture(x0)
         self._static_x0.copy_(x0, non_blocking=True)
-        self._graph.replay()
+        if self.split_graph:
+            self._weights(x0.shape[0])
+            self._graph.replay()
+            if self.world > 1:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+            self._graph_update.replay()
+        else:
+            self._graph.replay()
         return DeferredMetrics(self._static_metrics.clone())
 
     def synthetic_batch(self) -> torch.Tensor:

@@ -78,6 +78,7 @@ def distributional_training_step(
     group=None,
     sync_metrics: bool = True,
     fused_io: Optional[bool] = None,
+    weight_sum: Optional[torch.Tensor] = None,
 ):
     """Generalized energy training loss (paper eqs. 12-14) — reference ``dddm/training.py:32-93``.
 
@@ -91,6 +92,8 @@ def distributional_training_step(
       the GLOBAL batch — one float all-reduce of sum_b w(t_b) issued before the backbone forward —
       so that a batch-sharded run equals the single-process global batch (the
       reference's loss is a product of two batch means).  Defaults to on when world_size > 1;
+    * ``weight_sum``: sum_b w(t_b) over the GLOBAL batch, already all-reduced by the caller (the launcher does
+      this outside its CUDA graphs); K4 and the all-reduce are then skipped.  Requires ``t``;
     * ``sync_metrics=False`` returns a :class:`DeferredMetrics` (no host synchronisation in the step);
     * ``fused_io`` (default: on when the model offers ``forward_cat``/``patch_size``, i.e. ``ddm_b200.backbones
       .DDDMDiT``, and ``x0`` is an image batch): K2c writes cat(x_t, xi) m-fold directly in the backbone's compute
@@ -114,14 +117,17 @@ def distributional_training_step(
         xi = torch.randn((batch, m, *x0.shape[1:]), device=device, dtype=dtype)
 
     # logistic weight: per-rank sum now, (async) global sum while the backbone runs
-    _, w_sum = ops.sigmoid_weight_sum(t, float(w_bias))
     world = _world(group)
     use_global = (world > 1) if global_weight is None else (bool(global_weight) and world > 1)
     work = None
-    if use_global:
-        import torch.distributed as dist
+    if weight_sum is not None:
+        w_sum = weight_sum.reshape(-1)[:1]
+    else:
+        _, w_sum = ops.sigmoid_weight_sum(t, float(w_bias))
+        if use_global:
+            import torch.distributed as dist
 
-        work = dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=group, async_op=True)
+            work = dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=group, async_op=True)
     weight_scale = 1.0 / (batch * (world if use_global else 1))
 
     t_rep = t.repeat_interleave(m)
