@@ -53,6 +53,13 @@ SIGNATURES = {
                                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dddm_forward_marginal_concat_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                                   c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dddm_backbone_scratch_bytes": (c_size_t, [c_int]),
+    "dddm_layer_norm_fwd_f32": (c_int, [c_void_p] * 6 + [c_long, c_int, c_float, c_void_p]),
+    "dddm_layer_norm_fwd_bf16": (c_int, [c_void_p] * 6 + [c_long, c_int, c_float, c_void_p]),
+    "dddm_layer_norm_bwd_f32": (c_int, [c_void_p] * 9 + [c_size_t, c_long, c_int, c_void_p]),
+    "dddm_layer_norm_bwd_bf16": (c_int, [c_void_p] * 9 + [c_size_t, c_long, c_int, c_void_p]),
+    "dddm_colsum_f32": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
+    "dddm_colsum_bf16": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
     "dddm_sigmoid_weight_sum_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "dddm_bridge_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
                                      c_void_p, c_void_p, c_long, c_long, c_void_p]),

@@ -14,7 +14,10 @@ checkpoint's ``state_dict`` loads.  Same math, arranged for throughput (SURVEY.m
 * LayerNorm applies its affine outside the normalisation kernel: ATen's gamma/beta backward kernel
   took 0.56 ms per LayerNorm at this shape (9.6 ms / step, the largest single item); two plain
   reductions replace it;
-* the time embedding is always evaluated in fp32 (a bf16 ``t`` has 8 bits of resolution).
+* the time embedding is always evaluated in fp32 (a bf16 ``t`` has 8 bits of resolution);
+* on CUDA, LayerNorm forward/backward and the bias-gradient column sums of every Linear run on this repo's
+  kernels (``csrc/backbone_ops.cu``; ``USE_CUDA_KERNELS = False`` switches back to the plain ATen composition,
+  which is also what runs on CPU).
 """
 from __future__ import annotations
 
@@ -23,6 +26,43 @@ import math
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+USE_CUDA_KERNELS = True  # LayerNorm / bias-gradient kernels of csrc/backbone_ops.cu on CUDA tensors (training only)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b with the bias gradient reduced by ``ops.colsum`` (fixed-order column sums)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import ops
+
+        x, weight = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        gx = (g2 @ weight).view(x.shape) if ctx.needs_input_grad[0] else None
+        gw = g2.t() @ x.reshape(-1, x.shape[-1]) if ctx.needs_input_grad[1] else None
+        gb = None
+        if ctx.needs_input_grad[2]:
+            g2c = g2.contiguous()
+            gb = ops.colsum(g2c) if ops.colsum_supported(g2c) else g2c.sum(dim=0)
+        return gx, gw, gb
+
+
+def _linear(x, weight, bias):
+    if USE_CUDA_KERNELS and x.is_cuda and bias is not None and torch.is_grad_enabled() and x.dtype == weight.dtype:
+        return _LinearFn.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+class _Linear(nn.Linear):
+    def forward(self, x):
+        return _linear(x, self.weight, self.bias)
 
 
 class _FourierTime(nn.Module):
@@ -77,6 +117,11 @@ class _LayerNorm(nn.LayerNorm):
     def forward(self, x):
         if not torch.is_grad_enabled():  # inference (sampler): the single fused ATen kernel is the fastest form
             return F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        if USE_CUDA_KERNELS and x.is_cuda:
+            from . import ops
+
+            if ops.layer_norm_supported(x, self.weight, self.bias):
+                return ops.layer_norm(x, self.weight, self.bias, self.eps)[0]
         xn = F.layer_norm(x, self.normalized_shape, None, None, self.eps)
         return torch.addcmul(self.bias, xn, self.weight)
 
@@ -87,8 +132,8 @@ class _Attention(nn.Module):
         if dim % heads:
             raise ValueError("dim must be divisible by num_heads")
         self.heads = heads
-        self.qkv = nn.Linear(dim, 3 * dim)
-        self.proj = nn.Linear(dim, dim)
+        self.qkv = _Linear(dim, 3 * dim)
+        self.proj = _Linear(dim, dim)
 
     def forward(self, x):
         b, n, c = x.shape
@@ -96,7 +141,7 @@ class _Attention(nn.Module):
             q, k, v = self.qkv(x).view(b, n, 3, self.heads, c // self.heads).permute(2, 0, 3, 1, 4)
             return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c))
         w, bias = self.qkv.weight, self.qkv.bias
-        q, k, v = (F.linear(x, w[i * c:(i + 1) * c], bias[i * c:(i + 1) * c]).view(b, n, self.heads, c // self.heads)
+        q, k, v = (_linear(x, w[i * c:(i + 1) * c], bias[i * c:(i + 1) * c]).view(b, n, self.heads, c // self.heads)
                    .transpose(1, 2) for i in range(3))
         y = F.scaled_dot_product_attention(q, k, v)
         return self.proj(y.transpose(1, 2).reshape(b, n, c))
@@ -105,7 +150,7 @@ class _Attention(nn.Module):
 class _MLP(nn.Module):
     def __init__(self, dim: int, hidden: int):
         super().__init__()
-        self.net = nn.Sequential(nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim))
+        self.net = nn.Sequential(_Linear(dim, hidden), nn.GELU(), _Linear(hidden, dim))
 
     def forward(self, x):
         return self.net(x)
@@ -138,10 +183,10 @@ class DDDMDiT(nn.Module):
         self.grid = img_size // patch_size
         self.patch_embed = _Proj(nn.Conv2d(in_channels, embed_dim, kernel_size=patch_size, stride=patch_size))
         self.pos_embed = nn.Parameter(torch.zeros(1, self.grid * self.grid, embed_dim))
-        self.time_mlp = nn.Sequential(nn.Linear(time_embed_dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, embed_dim))
+        self.time_mlp = nn.Sequential(_Linear(time_embed_dim, embed_dim), nn.SiLU(), _Linear(embed_dim, embed_dim))
         self.blocks = nn.ModuleList(_Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth))
         self.norm = _LayerNorm(embed_dim)
-        self.unembed = _Proj(nn.Linear(embed_dim, out_channels * patch_size * patch_size))
+        self.unembed = _Proj(_Linear(embed_dim, out_channels * patch_size * patch_size))
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
 
     def forward(self, xt, t, xi):

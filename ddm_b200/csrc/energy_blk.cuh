@@ -128,7 +128,6 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     constexpr int NSWEEP = NB / 2 + NB * (NB - 1) / 2;  // M = 16: 2, M = 32: 8
     const int nsplit = max(1, nwarps / NSWEEP);         // column splits (M = 16 with 4 warps: 2)
     if (!control) {
-        const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
         int waited = -1;  // chunks this thread has already waited for
         for (int unit = warp; unit < NSWEEP * nsplit; unit += nwarps) {
             const int sweep = unit / nsplit, split = unit - sweep * nsplit;

@@ -374,3 +374,101 @@ def bridge_mu_sigma(s: Tensor, t: Tensor, x0: Tensor, xt: Tensor, eps_churn: flo
 @bridge_mu_sigma.register_fake
 def _(s, t, x0, xt, eps_churn):
     return torch.empty_like(xt), xt.new_empty(max(s.numel(), t.numel()), dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------
+# Backbone helpers: LayerNorm forward/backward and column sums for the DiT step
+# --------------------------------------------------------------------------------------------
+def _scratch(ref: Tensor, C: int) -> Tensor:
+    return torch.empty(_cabi.lib().dddm_backbone_scratch_bytes(C), dtype=torch.uint8, device=ref.device)
+
+
+def layer_norm_supported(x: Tensor, weight: Tensor, bias: Tensor) -> bool:
+    C = x.shape[-1]
+    return (x.is_cuda and x.dtype in _SUFFIX and weight is not None and bias is not None and weight.dtype == x.dtype
+            and bias.dtype == x.dtype and C % 4 == 0 and 4 <= C <= 1024 and (C * x.element_size()) % 16 == 0)
+
+
+@torch.library.custom_op("ddm_b200::layer_norm", mutates_args=())
+def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """LayerNorm over the last dimension: returns (y like x, mean [N] fp32, rstd [N] fp32)."""
+    _require_cuda(x, weight, bias)
+    sfx = _suffix(x)
+    x = x.contiguous()
+    C = x.shape[-1]
+    N = x.numel() // C
+    y = torch.empty_like(x)
+    mean = torch.empty(N, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        fn = getattr(_cabi.lib(), f"dddm_layer_norm_fwd_{sfx}")
+        _cabi.check(fn(_ptr(x), _ptr(weight.contiguous()), _ptr(bias.contiguous()), _ptr(y), _ptr(mean), _ptr(rstd), N, C,
+                       float(eps), _stream(x)))
+    return y, mean, rstd
+
+
+@layer_norm.register_fake
+def _(x, weight, bias, eps):
+    N = x.numel() // x.shape[-1]
+    return torch.empty_like(x), x.new_empty(N, dtype=torch.float32), x.new_empty(N, dtype=torch.float32)
+
+
+@torch.library.custom_op("ddm_b200::layer_norm_bwd", mutates_args=())
+def layer_norm_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, weight: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    _require_cuda(dy, x, mean, rstd, weight)
+    sfx = _suffix(x)
+    dy, x = dy.contiguous(), x.contiguous()
+    C = x.shape[-1]
+    N = x.numel() // C
+    dx = torch.empty_like(x)
+    dw, db = torch.empty_like(weight), torch.empty_like(weight)
+    with torch.cuda.device(x.device):
+        scratch = _scratch(x, C)
+        fn = getattr(_cabi.lib(), f"dddm_layer_norm_bwd_{sfx}")
+        _cabi.check(fn(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(weight.contiguous()), _ptr(dx), _ptr(dw), _ptr(db),
+                       _ptr(scratch), scratch.numel(), N, C, _stream(x)))
+    return dx, dw, db
+
+
+@layer_norm_bwd.register_fake
+def _(dy, x, mean, rstd, weight):
+    return torch.empty_like(x), torch.empty_like(weight), torch.empty_like(weight)
+
+
+def _ln_setup(ctx, inputs, output):
+    x, weight, bias, eps = inputs
+    ctx.save_for_backward(x, output[1], output[2], weight)
+
+
+def _ln_backward(ctx, gy, gmean, grstd):
+    x, mean, rstd, weight = ctx.saved_tensors
+    dx, dw, db = layer_norm_bwd(gy, x, mean, rstd, weight)
+    return dx, dw, db, None
+
+
+layer_norm.register_autograd(_ln_backward, setup_context=_ln_setup)
+
+
+def colsum_supported(a: Tensor) -> bool:
+    C = a.shape[-1]
+    return a.is_cuda and a.dtype in _SUFFIX and a.dim() == 2 and C % 4 == 0 and (C * a.element_size()) % 16 == 0 and a.shape[0] > 0
+
+
+@torch.library.custom_op("ddm_b200::colsum", mutates_args=())
+def colsum(a: Tensor) -> Tensor:
+    """out[c] = sum_n a[n, c] (fp32 accumulation, fixed summation order), same dtype as ``a``."""
+    _require_cuda(a)
+    sfx = _suffix(a)
+    a = a.contiguous()
+    N, C = a.shape
+    out = torch.empty(C, dtype=a.dtype, device=a.device)
+    with torch.cuda.device(a.device):
+        scratch = _scratch(a, C)
+        fn = getattr(_cabi.lib(), f"dddm_colsum_{sfx}")
+        _cabi.check(fn(_ptr(a), _ptr(out), _ptr(scratch), scratch.numel(), N, C, _stream(a)))
+    return out
+
+
+@colsum.register_fake
+def _(a):
+    return a.new_empty(a.shape[1])

@@ -177,6 +177,30 @@ void dddm_host_free(void*);
 int dddm_last_error(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Backbone helpers for the DiT training step (the backbone itself stays PyTorch).  These replace the
+ * two HBM-bound items that dominated its profile at 65 536 tokens x 384 channels (profiles/r01_dit.md):
+ *   LayerNorm forward / backward (torch.nn.functional.layer_norm semantics, dddm/model.py:158-163, 203: biased variance,
+ *   eps inside the square root; mean/rstd [N] fp32 saved for the backward; dgamma/dbeta reduced in a fixed order), and
+ *   column sums out[c] = sum_n a[n, c] (bias gradients of every Linear).
+ * x, y, dy, dx: [N, C] contiguous, C % 4 == 0, rows 16-byte aligned, C <= 1024 for LayerNorm.  scratch: at least
+ * dddm_backbone_scratch_bytes(C) bytes of device memory (no initialisation needed).
+ * ------------------------------------------------------------------------------------------ */
+size_t dddm_backbone_scratch_bytes(int C);
+int dddm_layer_norm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                            long N, int C, float eps, dddm_stream_t stream);
+int dddm_layer_norm_fwd_bf16(const dddm_bf16* x, const dddm_bf16* gamma, const dddm_bf16* beta, dddm_bf16* y, float* mean,
+                             float* rstd, long N, int C, float eps, dddm_stream_t stream);
+int dddm_layer_norm_bwd_f32(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            float* dx, float* dgamma, float* dbeta, float* scratch, size_t scratch_bytes, long N, int C,
+                            dddm_stream_t stream);
+int dddm_layer_norm_bwd_bf16(const dddm_bf16* dy, const dddm_bf16* x, const float* mean, const float* rstd,
+                             const dddm_bf16* gamma, dddm_bf16* dx, dddm_bf16* dgamma, dddm_bf16* dbeta, float* scratch,
+                             size_t scratch_bytes, long N, int C, dddm_stream_t stream);
+int dddm_colsum_f32(const float* a, float* out, float* scratch, size_t scratch_bytes, long N, int C, dddm_stream_t stream);
+int dddm_colsum_bf16(const dddm_bf16* a, dddm_bf16* out, float* scratch, size_t scratch_bytes, long N, int C,
+                     dddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tuning / introspection (benchmarks and tests; never needed for correctness).
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
  *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto),
