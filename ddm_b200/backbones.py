@@ -60,6 +60,37 @@ def _linear(x, weight, bias):
     return F.linear(x, weight, bias)
 
 
+class _QKVFn(torch.autograd.Function):
+    """q, k, v = x W_q^T + b_q, ... from row-slices of ONE packed weight (state-dict layout of the reference), as three
+    GEMMs so that each of q/k/v is a dense [B, n, C] tensor SDPA can view as [B, n, h, d] without copies.  Backward
+    accumulates dX over the three branches inside the GEMM epilogue (addmm, beta = 1) instead of two extra passes, and
+    writes dW / db straight into the three row-slices of the packed gradients."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        c = x.shape[-1]
+        ctx.save_for_backward(x, weight)
+        return tuple(F.linear(x, weight[i * c:(i + 1) * c], bias[i * c:(i + 1) * c]) for i in range(3))
+
+    @staticmethod
+    def backward(ctx, gq, gk, gv):
+        from . import ops
+
+        x, weight = ctx.saved_tensors
+        c = x.shape[-1]
+        x2 = x.reshape(-1, c)
+        gs = [g.reshape(-1, c).contiguous() for g in (gq, gk, gv)]
+        gx = gs[0] @ weight[:c]
+        gx.addmm_(gs[1], weight[c:2 * c])
+        gx.addmm_(gs[2], weight[2 * c:])
+        gw = torch.empty_like(weight)
+        gb = torch.empty(3 * c, dtype=weight.dtype, device=weight.device)
+        for i, g in enumerate(gs):
+            torch.mm(g.t(), x2, out=gw[i * c:(i + 1) * c])
+            gb[i * c:(i + 1) * c] = ops.colsum(g) if ops.colsum_supported(g) else g.sum(dim=0)
+        return gx.view(x.shape), gw, gb
+
+
 class _Linear(nn.Linear):
     def forward(self, x):
         return _linear(x, self.weight, self.bias)
@@ -126,6 +157,18 @@ class _LayerNorm(nn.LayerNorm):
         return torch.addcmul(self.bias, xn, self.weight)
 
 
+def _sdpa(q, k, v):
+    """Short sequences (64 tokens here): the memory-efficient backend is ~1.7x faster than cuDNN's flash kernels on
+    B200 for fwd+bwd at [1024, 6, 64, 64] and returns dq/dk/dv in the layout of its inputs (no re-layout copies)."""
+    if q.is_cuda and q.shape[-2] <= 256 and q.dtype in (torch.bfloat16, torch.float16):
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        with sdpa_kernel([SDPBackend.EFFICIENT_ATTENTION, SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION,
+                          SDPBackend.MATH], set_priority=True):
+            return F.scaled_dot_product_attention(q, k, v)
+    return F.scaled_dot_product_attention(q, k, v)
+
+
 class _Attention(nn.Module):
     def __init__(self, dim: int, heads: int):
         super().__init__()
@@ -139,12 +182,14 @@ class _Attention(nn.Module):
         b, n, c = x.shape
         if not torch.is_grad_enabled():  # inference: one GEMM, q/k/v as strided views
             q, k, v = self.qkv(x).view(b, n, 3, self.heads, c // self.heads).permute(2, 0, 3, 1, 4)
-            return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c))
+            return self.proj(_sdpa(q, k, v).transpose(1, 2).reshape(b, n, c))
         w, bias = self.qkv.weight, self.qkv.bias
-        q, k, v = (_linear(x, w[i * c:(i + 1) * c], bias[i * c:(i + 1) * c]).view(b, n, self.heads, c // self.heads)
-                   .transpose(1, 2) for i in range(3))
-        y = F.scaled_dot_product_attention(q, k, v)
-        return self.proj(y.transpose(1, 2).reshape(b, n, c))
+        if USE_CUDA_KERNELS and x.is_cuda and x.dtype == w.dtype:
+            qkv = _QKVFn.apply(x, w, bias)
+        else:
+            qkv = tuple(F.linear(x, w[i * c:(i + 1) * c], bias[i * c:(i + 1) * c]) for i in range(3))
+        q, k, v = (t.view(b, n, self.heads, c // self.heads).transpose(1, 2) for t in qkv)
+        return self.proj(_sdpa(q, k, v).transpose(1, 2).reshape(b, n, c))
 
 
 class _MLP(nn.Module):
@@ -202,7 +247,9 @@ class DDDMDiT(nn.Module):
         PatchUnembed's projection ``[B, (H/p)(W/p), C*p*p]`` without the unpatchify permute/copy: the energy
         score only needs x0 in the same order (K2c provides it)."""
         wdtype = self.patch_embed.proj.weight.dtype
-        emb = self.patch_embed.proj(x6.to(wdtype)).flatten(2).transpose(1, 2)
+        # .contiguous(): the conv output viewed as tokens is a permuted-stride tensor; left as is, the whole residual
+        # stream inherits those strides and every LayerNorm / Linear pays a 50 MB re-layout copy (34 per step)
+        emb = self.patch_embed.proj(x6.to(wdtype)).flatten(2).transpose(1, 2).contiguous()
         temb = self.time_mlp(_sinusoidal(t.reshape(-1).float(), self.time_embed_dim).to(wdtype))
         h = emb + temb[:, None, :] + self.pos_embed
         for blk in self.blocks:

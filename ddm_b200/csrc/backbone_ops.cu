@@ -169,25 +169,32 @@ layer_norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const f
     }
 }
 
-// out[c] = sum_p part[p][c]  (fixed order), c < width; written as T
+// out[c] = sum_p part[p][c] in a fixed order, c < width; written as T.  32 columns x 8 part-phases per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256)
 fold_partials_kernel(const float* __restrict__ part, int nparts, int width, T* __restrict__ out0, T* __restrict__ out1,
                      int split) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= width) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int p = 0;
-    for (; p + 3 < nparts; p += 4) {
-        a0 += part[(size_t)p * width + c];
-        a1 += part[(size_t)(p + 1) * width + c];
-        a2 += part[(size_t)(p + 2) * width + c];
-        a3 += part[(size_t)(p + 3) * width + c];
+    __shared__ float s_acc[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < width) {
+        int p = ty;
+        for (; p + 8 < nparts; p += 16) {
+            a0 += part[(size_t)p * width + c];
+            a1 += part[(size_t)(p + 8) * width + c];
+        }
+        if (p < nparts) a0 += part[(size_t)p * width + c];
     }
-    for (; p < nparts; ++p) a0 += part[(size_t)p * width + c];
-    const float t = (a0 + a1) + (a2 + a3);
-    if (c < split) out0[c] = Elem<T>::from_float(t);
-    else out1[c - split] = Elem<T>::from_float(t);
+    s_acc[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty == 0 && c < width) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_acc[k][tx];
+        if (c < split) out0[c] = Elem<T>::from_float(t);
+        else out1[c - split] = Elem<T>::from_float(t);
+    }
 }
 
 // Column sums of a [N, C] matrix: CTA (bx, by) sums rows by, by + gridDim.y, ... of 4-column groups.
@@ -268,7 +275,7 @@ static int ln_bwd_nv(const T* dy, const T* x, const float* mean, const float* rs
     }
     kernel<<<grid, kLnWarps * 32, smem, stream>>>(dy, x, mean, rstd, gamma, dx, part, N, C);
     count_launch();
-    fold_partials_kernel<T><<<(2 * C + 255) / 256, 256, 0, stream>>>(part, grid, 2 * C, dgamma, dbeta, C);
+    fold_partials_kernel<T><<<(2 * C + 31) / 32, 256, 0, stream>>>(part, grid, 2 * C, dgamma, dbeta, C);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -305,7 +312,7 @@ static int colsum(const T* a, T* out, float* part, size_t part_bytes, long N, in
     if ((size_t)gy * per > part_bytes) gy = (long)(part_bytes / per);
     colsum_partial_kernel<T><<<dim3(gx, (unsigned)gy), 256, 0, stream>>>(a, part, N, C);
     count_launch();
-    fold_partials_kernel<T><<<(C + 255) / 256, 256, 0, stream>>>(part, (int)gy, C, out, out, C);
+    fold_partials_kernel<T><<<(C + 31) / 32, 256, 0, stream>>>(part, (int)gy, C, out, out, C);
     count_launch();
     return (int)cudaGetLastError();
 }
