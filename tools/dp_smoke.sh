@@ -17,6 +17,6 @@ except Exception as e:
     print("no bench line:", e)
 PY
 timeout 240 $TR --master-port 29512 -m ddm_b200.launcher --synthetic --epochs 2 --steps-per-epoch 30 --log-every 10 \
-    --out gpurun_out/dp_run_n$N --sample-batch 16 --sample-steps 5 2>gpurun_out/launcher_n$N.err | tail -6
+    --out /tmp/dp_run_n$N --sample-batch 16 --sample-steps 5 2>gpurun_out/launcher_n$N.err | tail -6
 echo "launcher rc=${PIPESTATUS[0]}"
-ls gpurun_out/dp_run_n$N
+ls /tmp/dp_run_n$N; cp /tmp/dp_run_n$N/train_history.json gpurun_out/train_history_n$N.json
