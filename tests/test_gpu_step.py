@@ -350,3 +350,18 @@ def test_fused_io_step_equals_generic_step(dev):
         assert float((ga - gb).abs().max()) <= tol * float(gb.abs().max()), (dtype, float((ga - gb).abs().max()))
     with pytest.raises(ValueError):
         ddm_b200.distributional_training_step(MixModel().to(dev), x0, m=m, beta=0.1, lam=1.0, w_bias=0.0, fused_io=True)
+
+
+def test_sampler_cuda_graph_equals_eager(dev):
+    """sample_dddm(cuda_graph=True): same Philox stream, same draws, same result as the eager loop."""
+    import ddm_b200
+
+    model = MixModel().to(dev)
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(123)
+        outs.append(ddm_b200.sample_dddm(model, n_samples=64, steps=7, eps_churn=0.7, device=str(dev), data_shape=(3, 8, 8),
+                                         cuda_graph=graph))
+        tail = torch.randn(4, device=dev)  # the generator must end at the same position
+        outs.append(tail)
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
