@@ -6,6 +6,7 @@ function signatures as the reference's ``dddm.losses`` / ``dddm.schedules`` / ``
 modules without the built library (``python -m ddm_b200.build``) fails loudly on first use.
 """
 from .losses import generalized_energy_terms, sigmoid_weight
+from .metrics import rbf_mmd2
 from .patch import patch_reference, unpatch_reference
 from .sampling import sample_dddm, sample_dddm_sharded
 from .schedules import alpha_sigma, forward_marginal_sample, gaussian_bridge_mu_sigma
@@ -14,5 +15,5 @@ from .training import DeferredMetrics, TrainConfig, distributional_training_step
 __all__ = [
     "generalized_energy_terms", "sigmoid_weight", "alpha_sigma", "forward_marginal_sample",
     "gaussian_bridge_mu_sigma", "sample_dddm", "sample_dddm_sharded", "distributional_training_step",
-    "TrainConfig", "DeferredMetrics", "patch_reference", "unpatch_reference",
+    "TrainConfig", "DeferredMetrics", "patch_reference", "unpatch_reference", "rbf_mmd2",
 ]

@@ -60,6 +60,10 @@ SIGNATURES = {
     "dddm_layer_norm_bwd_bf16": (c_int, [c_void_p] * 9 + [c_size_t, c_long, c_int, c_void_p]),
     "dddm_colsum_f32": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
     "dddm_colsum_bf16": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
+    "dddm_row_sqnorm_f32": (c_int, [c_void_p, c_void_p, c_long, c_long, c_void_p]),
+    "dddm_rbf_scratch_bytes": (c_size_t, [c_long, c_long]),
+    "dddm_rbf_kernel_sum_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_long, c_long, c_float, c_long, c_int,
+                                        c_void_p, c_size_t, c_void_p, c_void_p]),
     "dddm_sigmoid_weight_sum_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "dddm_bridge_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
                                      c_void_p, c_void_p, c_long, c_long, c_void_p]),

@@ -1,0 +1,43 @@
+"""Drop-in for ``dddm/metrics.py::rbf_mmd2`` (evaluation side of the path)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_ROW_CHUNK = 8192  # rows of the Gram matrix formed at a time: 8192 x 10 000 fp32 = 328 MB
+
+
+def _kernel_sum(a: torch.Tensor, b: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor, gamma: float, skip_diag: bool):
+    total = torch.zeros(1, dtype=torch.float64, device=a.device)
+    for r0 in range(0, a.shape[0], _ROW_CHUNK):
+        rows = a[r0:r0 + _ROW_CHUNK]
+        gram = rows @ b.t()  # library GEMM (cuBLAS), fp32 like the reference's `a @ b.T` (metrics.py:146)
+        total += ops.rbf_kernel_sum(gram, a2[r0:r0 + _ROW_CHUNK], b2, gamma, r0, skip_diag)
+    return total
+
+
+@torch.no_grad()
+def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+    """Unbiased MMD^2 with an RBF kernel, sigma fixed — reference ``dddm/metrics.py:140-163``.
+
+    Same signature, ``ValueError`` for fewer than two samples per set, 0-dim result in the input dtype.  The three
+    n x n terms are never materialised beyond one Gram tile each: GEMM tile -> one fused pass (distance, exp,
+    diagonal mask, sum).  CUDA-only; not differentiable (the reference only calls it on detached samples,
+    ``run_example.py:101``).
+    """
+    if not (x.is_cuda and y.is_cuda):
+        raise RuntimeError("ddm_b200.rbf_mmd2 runs on CUDA tensors only (no CPU fallback)")
+    n, m = x.size(0), y.size(0)
+    if n < 2 or m < 2:
+        raise ValueError("Need at least two samples per set to compute MMD")
+    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
+        raise ValueError(f"expected x [n, D] and y [m, D], got {tuple(x.shape)} and {tuple(y.shape)}")
+    dtype = x.dtype
+    xf, yf = x.detach().float().contiguous(), y.detach().float().contiguous()
+    gamma = 1.0 / (2.0 * sigma**2)
+    x2, y2 = ops.row_sqnorm(xf), ops.row_sqnorm(yf)
+    kxx = _kernel_sum(xf, xf, x2, x2, gamma, True) / (n * (n - 1))
+    kyy = _kernel_sum(yf, yf, y2, y2, gamma, True) / (m * (m - 1))
+    kxy = _kernel_sum(xf, yf, x2, y2, gamma, False) / (n * m)
+    return (kxx + kyy - 2.0 * kxy).reshape(()).to(dtype)

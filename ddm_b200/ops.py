@@ -472,3 +472,47 @@ def colsum(a: Tensor) -> Tensor:
 @colsum.register_fake
 def _(a):
     return a.new_empty(a.shape[1])
+
+
+# --------------------------------------------------------------------------------------------
+# Evaluation: pairwise RBF kernel sums for rbf_mmd2  (dddm/metrics.py:140-163)
+# --------------------------------------------------------------------------------------------
+@torch.library.custom_op("ddm_b200::row_sqnorm", mutates_args=())
+def row_sqnorm(x: Tensor) -> Tensor:
+    _require_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError("row_sqnorm expects a 2-D float32 tensor")
+    x = x.contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(_cabi.lib().dddm_row_sqnorm_f32(_ptr(x), _ptr(out), x.shape[0], x.shape[1], _stream(x)))
+    return out
+
+
+@row_sqnorm.register_fake
+def _(x):
+    return x.new_empty(x.shape[0])
+
+
+@torch.library.custom_op("ddm_b200::rbf_kernel_sum", mutates_args=())
+def rbf_kernel_sum(gram: Tensor, a2: Tensor, b2: Tensor, gamma: float, diag_shift: int, skip_diag: bool) -> Tensor:
+    """sum over the tile of exp(-gamma (a2_r + b2_c - 2 G_rc)), skipping r + diag_shift == c when skip_diag; fp64 [1]."""
+    _require_cuda(gram, a2, b2)
+    if gram.dtype != torch.float32 or gram.dim() != 2 or gram.stride(1) != 1:
+        raise TypeError("rbf_kernel_sum expects a row-major float32 Gram tile")
+    rows, cols = gram.shape
+    a2, b2 = a2.float().contiguous(), b2.float().contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=gram.device)
+    with torch.cuda.device(gram.device):
+        L = _cabi.lib()
+        nbytes = L.dddm_rbf_scratch_bytes(rows, cols)
+        scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=gram.device)
+        _cabi.check(L.dddm_rbf_kernel_sum_f32(_ptr(gram), gram.stride(0), _ptr(a2), _ptr(b2), rows, cols, float(gamma),
+                                              int(diag_shift), int(bool(skip_diag)), _ptr(scratch), nbytes, _ptr(out),
+                                              _stream(gram)))
+    return out
+
+
+@rbf_kernel_sum.register_fake
+def _(gram, a2, b2, gamma, diag_shift, skip_diag):
+    return gram.new_empty(1, dtype=torch.float64)

@@ -13,14 +13,16 @@ from types import ModuleType
 from typing import Optional
 
 
-def patch_reference(dddm: Optional[ModuleType] = None, *, whole_step: bool = True, whole_sampler: bool = True) -> dict:
+def patch_reference(dddm: Optional[ModuleType] = None, *, whole_step: bool = True, whole_sampler: bool = True,
+                    metrics: bool = True) -> dict:
     """Rebind the reference package ``dddm`` (already importable) onto ``ddm_b200``.
 
     * always: ``dddm.losses.{generalized_energy_terms, sigmoid_weight}``,
       ``dddm.schedules.{forward_marginal_sample, gaussian_bridge_mu_sigma}`` and the copies of those
       names inside ``dddm.training`` / ``dddm.sampling``;
     * ``whole_step``: also ``distributional_training_step`` (fused K1 path) in ``dddm.training`` and ``dddm``;
-    * ``whole_sampler``: also ``sample_dddm`` in ``dddm.sampling`` and ``dddm``.
+    * ``whole_sampler``: also ``sample_dddm`` in ``dddm.sampling`` and ``dddm``;
+    * ``metrics``: also ``rbf_mmd2`` in ``dddm.metrics`` and ``dddm`` (``dddm/metrics.py:140``, used at ``run_example.py:101``).
 
     Returns {qualified name: original object} so the caller can undo it with :func:`unpatch_reference`.
     Scripts that did ``from dddm import sample_dddm`` before patching keep the old binding — patch first.
@@ -46,6 +48,11 @@ def patch_reference(dddm: Optional[ModuleType] = None, *, whole_step: bool = Tru
                  (dddm, "distributional_training_step", training.distributional_training_step)]
     if whole_sampler:
         plan += [(mods["sampling"], "sample_dddm", sampling.sample_dddm), (dddm, "sample_dddm", sampling.sample_dddm)]
+    if metrics:
+        from . import metrics as _metrics
+
+        plan += [(importlib.import_module(f"{dddm.__name__}.metrics"), "rbf_mmd2", _metrics.rbf_mmd2),
+                 (dddm, "rbf_mmd2", _metrics.rbf_mmd2)]
     saved = {}
     for mod, name, new in plan:
         saved[(mod, name)] = getattr(mod, name, None)

@@ -201,6 +201,20 @@ int dddm_colsum_bf16(const dddm_bf16* a, dddm_bf16* out, float* scratch, size_t 
                      dddm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation: rbf_mmd2 (dddm/metrics.py:140-163).  The Gram tile G = A B^T comes from the caller's
+ * library GEMM; dddm_rbf_kernel_sum_f32 makes ONE pass over it:
+ *   out[0] = sum_{r < rows, c < cols, not (skip_diag and r + diag_shift == c)} exp(-gamma * (a2[r] + b2[c] - 2 G[r, c]))
+ * (the reference's pdist2 + exp + boolean-mask gather + mean, metrics.py:143-162, without its five n x n temporaries).
+ * Partial sums are folded in double in a fixed order.  scratch: dddm_rbf_scratch_bytes(rows, cols) bytes.
+ * dddm_row_sqnorm_f32: out[i] = sum_k x[i, k]^2 (metrics.py:144-145).
+ * ------------------------------------------------------------------------------------------ */
+int dddm_row_sqnorm_f32(const float* x, float* out, long n, long D, dddm_stream_t stream);
+size_t dddm_rbf_scratch_bytes(long rows, long cols);
+int dddm_rbf_kernel_sum_f32(const float* G, long ldg, const float* a2, const float* b2, long rows, long cols, float gamma,
+                            long diag_shift, int skip_diag, double* scratch, size_t scratch_bytes, double* out,
+                            dddm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Tuning / introspection (benchmarks and tests; never needed for correctness).
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
  *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto),

@@ -152,3 +152,24 @@ def bridge_step(x, x0hat, z, s, t, eps_churn: float = 1.0):
     out, mu = np.empty_like(x2), np.empty_like(x2)
     lib().oracle_bridge_step(_p(x2), _p(h2), _p(zz), _p(ss), _p(tt), vec, float(eps_churn), N, D, _p(out), _p(mu))
     return out.reshape(xx.shape), mu.reshape(xx.shape)
+
+
+def rbf_mmd2(x, y, sigma: float = 1.0):
+    """numpy fp64 restatement of dddm/metrics.py:140-163 (unbiased MMD^2, RBF kernel, sigma fixed): the Gram-form
+    squared distances a2 + b2 - 2 a.b (:143-146), exp(-d2 / (2 sigma^2)), off-diagonal means for xx / yy (:157-160),
+    full mean for xy (:161).  Returns (mmd2, kxx, kyy, kxy)."""
+    x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    n, m = x.shape[0], y.shape[0]
+    if n < 2 or m < 2:
+        raise ValueError("Need at least two samples per set to compute MMD")
+    gamma = 1.0 / (2.0 * sigma**2)
+
+    def pdist2(a, b):
+        return (a * a).sum(-1)[:, None] + (b * b).sum(-1)[None, :] - 2.0 * (a @ b.T)
+
+    kxx_full = np.exp(-gamma * pdist2(x, x))
+    kyy_full = np.exp(-gamma * pdist2(y, y))
+    kxx = (kxx_full.sum() - np.trace(kxx_full)) / (n * (n - 1))
+    kyy = (kyy_full.sum() - np.trace(kyy_full)) / (m * (m - 1))
+    kxy = np.exp(-gamma * pdist2(x, y)).mean()
+    return kxx + kyy - 2.0 * kxy, kxx, kyy, kxy

@@ -52,6 +52,11 @@ def golden_sampler():
 
 
 @pytest.fixture(scope="session")
+def golden_mmd():
+    return load_golden("mmd.npz")
+
+
+@pytest.fixture(scope="session")
 def cuda_device():
     import torch
 

@@ -265,6 +265,35 @@ def sampler_cases(sampling):
     return out
 
 
+def mmd_cases():
+    """rbf_mmd2 (dddm/metrics.py:140-163) on seeded sets: the toy GMM shape (D=2, sigma=1, run_example.py:101),
+    a mid-dimensional case with a matched bandwidth, identical sets, and flattened images at sigma=1 (where every
+    off-diagonal kernel value underflows to 0, as in compute_image_mmd's default)."""
+    from dddm import metrics
+
+    out, names = {}, []
+    gen = torch.Generator().manual_seed(11)
+    cases = {
+        "toy": (torch.randn(600, 2, generator=gen) * 0.5 + torch.tensor([3.0, 3.0]),
+                torch.randn(500, 2, generator=gen) * 0.6 + torch.tensor([2.7, 3.1]), 1.0),
+        "mid": (torch.randn(300, 48, generator=gen), torch.randn(280, 48, generator=gen) * 1.1 + 0.1, 7.0),
+        "same": (None, None, 2.0),
+        "images": (torch.rand(12, 3072, generator=gen) * 2 - 1, torch.rand(10, 3072, generator=gen) * 2 - 1, 1.0),
+        "images_wide": (torch.rand(24, 3072, generator=gen) * 2 - 1, torch.rand(20, 3072, generator=gen) * 1.8 - 0.9, 40.0),
+    }
+    z = torch.randn(200, 5, generator=gen)
+    cases["same"] = (z, z.clone(), 2.0)
+    for name, (x, y, sigma) in cases.items():
+        v64 = metrics.rbf_mmd2(x.double(), y.double(), sigma)
+        v32 = metrics.rbf_mmd2(x.float(), y.float(), sigma)
+        out[f"{name}/x"], out[f"{name}/y"] = x.float().numpy(), y.float().numpy()
+        out[f"{name}/sigma"] = np.float64(sigma)
+        out[f"{name}/mmd2_f64"], out[f"{name}/mmd2_f32"] = v64.numpy(), v32.numpy()
+        names.append(name)
+    out["names"] = np.array(names)
+    return out
+
+
 def main():
     torch.set_num_threads(1)  # deterministic reductions for the recorded fp32 numbers
     losses, schedules, sampling, training = import_reference()
@@ -273,6 +302,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "schedules.npz"), **schedule_cases(schedules))
     np.savez_compressed(os.path.join(HERE, "step.npz"), **step_cases(training, schedules))
     np.savez_compressed(os.path.join(HERE, "sampler.npz"), **sampler_cases(sampling))
+    np.savez_compressed(os.path.join(HERE, "mmd.npz"), **mmd_cases())
     meta = f"torch {torch.__version__}, numpy {np.__version__}, reference at {REF}\n"
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write("Generated by tests/golden/make_golden.py from the unmodified reference functions.\n" + meta)

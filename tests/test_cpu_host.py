@@ -142,7 +142,7 @@ def test_patch_reference_rebinds_imported_names():
 
     pkg = types.ModuleType("fake_dddm")
     subs = {}
-    for name in ("losses", "schedules", "training", "sampling"):
+    for name in ("losses", "schedules", "training", "sampling", "metrics"):
         mod = types.ModuleType(f"fake_dddm.{name}")
         subs[name] = mod
         setattr(pkg, name, mod)
@@ -153,7 +153,8 @@ def test_patch_reference_rebinds_imported_names():
                        (subs["schedules"], ["forward_marginal_sample", "gaussian_bridge_mu_sigma"]),
                        (subs["training"], ["generalized_energy_terms", "sigmoid_weight", "forward_marginal_sample",
                                            "distributional_training_step"]),
-                       (subs["sampling"], ["gaussian_bridge_mu_sigma", "sample_dddm"])):
+                       (subs["sampling"], ["gaussian_bridge_mu_sigma", "sample_dddm"]),
+                       (subs["metrics"], ["rbf_mmd2"])):
         for n in names:
             setattr(mod, n, sentinel)
     try:
@@ -163,7 +164,9 @@ def test_patch_reference_rebinds_imported_names():
         assert subs["training"].distributional_training_step is ddm_b200.distributional_training_step
         assert subs["sampling"].gaussian_bridge_mu_sigma is ddm_b200.gaussian_bridge_mu_sigma
         assert pkg.sample_dddm is ddm_b200.sample_dddm
+        assert subs["metrics"].rbf_mmd2 is ddm_b200.rbf_mmd2 and pkg.rbf_mmd2 is ddm_b200.rbf_mmd2
         ddm_b200.unpatch_reference(saved)
+        assert subs["metrics"].rbf_mmd2 is sentinel
         assert subs["training"].sigmoid_weight is sentinel and not hasattr(pkg, "sample_dddm")
     finally:
         for k in [k for k in sys.modules if k.startswith("fake_dddm")]:

@@ -189,3 +189,15 @@ def test_sampler(golden_sampler):
             xx, _ = oracle.bridge_step(xx, xh, g[f"{n}/zs"][k], s, t, churn)
         assert np.allclose(xx, g[f"{n}/x_final"], rtol=2e-5, atol=2e-5), n
     assert tuple(g["default_shape"]) == (3, 2)
+
+
+def test_rbf_mmd2_oracle_matches_reference(golden_mmd):
+    """oracle.rbf_mmd2 (numpy fp64 restatement of dddm/metrics.py:140-163) against the reference's own outputs."""
+    g = golden_mmd
+    for n in [str(s) for s in g["names"]]:
+        mmd2, kxx, kyy, kxy = oracle.rbf_mmd2(g[f"{n}/x"], g[f"{n}/y"], float(g[f"{n}/sigma"]))
+        assert abs(mmd2 - float(g[f"{n}/mmd2_f64"])) <= 1e-12 * max(kxx, kyy, kxy, 1e-300) + 1e-300, n
+        # the reference's native fp32 run agrees to fp32 accuracy of the kernel means
+        assert abs(float(g[f"{n}/mmd2_f32"]) - mmd2) <= 2e-6 * max(kxx, kyy, kxy, 1e-30) + 1e-30, n
+    with pytest.raises(ValueError):
+        oracle.rbf_mmd2(np.zeros((1, 2)), np.zeros((3, 2)))
