@@ -206,6 +206,40 @@ def run_aux(args, dev, world) -> dict:
                 res[f"steps{nsteps}"] = {"samples_per_s": per * world / dt, "seconds": dt}
         aux["sampler"] = {"n_samples": per * world, "per_gpu": per, "model": "DDDMDiT(default)",
                           "launch": "one cached CUDA graph per Algorithm-2 step (captured by the warm-up call)", **res}
+    if args.mmd_samples > 0 and world == 1:
+        import ddm_b200
+
+        n = args.mmd_samples
+        gen = torch.Generator(device=dev).manual_seed(0)
+        xs = torch.rand(n, D, device=dev, generator=gen) * 2 - 1
+        ys = torch.rand(n, D, device=dev, generator=gen) * 1.9 - 0.95
+
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(reps):
+                out = fn()
+            m1.record()
+            m1.synchronize()
+            return m0.elapsed_time(m1) / reps, float(out)
+
+        ours_ms, ours_v = timed(lambda: ddm_b200.rbf_mmd2(xs, ys, 45.0))
+
+        def eager():  # the reference's formula (dddm/metrics.py:140-163) in eager PyTorch on the same GPU
+            def pd(a, b):
+                return (a * a).sum(-1).unsqueeze(-1) + (b * b).sum(-1).unsqueeze(0) - 2.0 * (a @ b.T)
+            g = 1.0 / (2.0 * 45.0**2)
+            mask = ~torch.eye(n, dtype=torch.bool, device=dev)
+            return torch.exp(-g * pd(xs, xs))[mask].mean() + torch.exp(-g * pd(ys, ys))[mask].mean() - 2.0 * torch.exp(
+                -g * pd(xs, ys)).mean()
+
+        ref_ms, ref_v = timed(eager)
+        aux["rbf_mmd2"] = {"n": n, "m": n, "D": D, "ms": ours_ms, "value": ours_v, "eager_reference_formula_ms": ref_ms,
+                           "eager_value": ref_v, "note": "evaluation-side pairwise kernel (SURVEY 8f-4): fp32 GEMM tiles "
+                           "(cuBLAS; only the upper trapezoids of the symmetric xx/yy terms) + one fused "
+                           "distance/exp/mask/sum pass per tile"}
     return aux
 
 
@@ -227,6 +261,7 @@ def main() -> None:
                     help="auxiliary: DP DiT training steps to time for the img/s figure (0 = skip)")
     ap.add_argument("--dit-precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--sampler-samples", type=int, default=1024, help="auxiliary: Algorithm-2 samples (0 = skip)")
+    ap.add_argument("--mmd-samples", type=int, default=10000, help="auxiliary: rbf_mmd2 set size (0 = skip)")
     ap.add_argument("--aux-timeout", type=float, default=240.0, help="seconds the auxiliary measurements may take")
     args = ap.parse_args()
     if args.impl == "reference":

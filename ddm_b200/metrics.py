@@ -5,15 +5,30 @@ import torch
 
 from . import ops
 
-_ROW_CHUNK = 8192  # rows of the Gram matrix formed at a time: 8192 x 10 000 fp32 = 328 MB
+_ROW_CHUNK = 8192   # rows of a rectangular Gram tile: 8192 x 10 000 fp32 = 328 MB
+_SYM_CHUNK = 2048   # rows of a trapezoidal tile of a symmetric term
 
 
-def _kernel_sum(a: torch.Tensor, b: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor, gamma: float, skip_diag: bool):
+def _kernel_sum(a: torch.Tensor, b: torch.Tensor, a2: torch.Tensor, b2: torch.Tensor, gamma: float) -> torch.Tensor:
+    """sum_{i,j} k(a_i, b_j) over the full rectangle (the xy term, metrics.py:161)."""
     total = torch.zeros(1, dtype=torch.float64, device=a.device)
     for r0 in range(0, a.shape[0], _ROW_CHUNK):
-        rows = a[r0:r0 + _ROW_CHUNK]
-        gram = rows @ b.t()  # library GEMM (cuBLAS), fp32 like the reference's `a @ b.T` (metrics.py:146)
-        total += ops.rbf_kernel_sum(gram, a2[r0:r0 + _ROW_CHUNK], b2, gamma, r0, skip_diag)
+        gram = a[r0:r0 + _ROW_CHUNK] @ b.t()  # library GEMM (cuBLAS), fp32 like the reference's `a @ b.T` (metrics.py:146)
+        total += ops.rbf_kernel_sum(gram, a2[r0:r0 + _ROW_CHUNK], b2, gamma, 0, False)
+    return total
+
+
+def _kernel_sum_offdiag(a: torch.Tensor, a2: torch.Tensor, gamma: float) -> torch.Tensor:
+    """sum_{i != j} k(a_i, a_j) (the xx / yy terms, metrics.py:157-160).  The matrix is symmetric: only the
+    trapezoid right of each diagonal block is formed (0.6x the GEMM work at n = 10 000), counted twice."""
+    n = a.shape[0]
+    total = torch.zeros(1, dtype=torch.float64, device=a.device)
+    for r0 in range(0, n, _SYM_CHUNK):
+        r1 = min(r0 + _SYM_CHUNK, n)
+        gram = a[r0:r1] @ a[r0:].t()  # [r1 - r0, n - r0]
+        total += ops.rbf_kernel_sum(gram[:, :r1 - r0], a2[r0:r1], a2[r0:r1], gamma, 0, True)
+        if r1 < n:
+            total += 2.0 * ops.rbf_kernel_sum(gram[:, r1 - r0:], a2[r0:r1], a2[r1:], gamma, 0, False)
     return total
 
 
@@ -37,7 +52,7 @@ def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tens
     xf, yf = x.detach().float().contiguous(), y.detach().float().contiguous()
     gamma = 1.0 / (2.0 * sigma**2)
     x2, y2 = ops.row_sqnorm(xf), ops.row_sqnorm(yf)
-    kxx = _kernel_sum(xf, xf, x2, x2, gamma, True) / (n * (n - 1))
-    kyy = _kernel_sum(yf, yf, y2, y2, gamma, True) / (m * (m - 1))
-    kxy = _kernel_sum(xf, yf, x2, y2, gamma, False) / (n * m)
+    kxx = _kernel_sum_offdiag(xf, x2, gamma) / (n * (n - 1))
+    kyy = _kernel_sum_offdiag(yf, y2, gamma) / (m * (m - 1))
+    kxy = _kernel_sum(xf, yf, x2, y2, gamma) / (n * m)
     return (kxx + kyy - 2.0 * kxy).reshape(()).to(dtype)
