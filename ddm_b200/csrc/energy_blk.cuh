@@ -74,25 +74,28 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     const int chunk_q = chunk_vecs * U;
     for (int s = tid; s < kBlkMaxSplit * P; s += blockDim.x) s_warp[s] = 0.f;
     if (control && lane == 0) {
-        for (int c = 0; c < nchunks; ++c) mbar_init(&s_bar[c], 1);
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_init(&s_bar[c], 1);
+            mbar_expect_tx(&s_bar[c], (uint32_t)min(chunk_vecs, nv - c * chunk_vecs) * 16u * (uint32_t)(M + 1));
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     cudaGridDependencySynchronize();
-    if (control) {
-        // rows 0..M-1 = draws, row M = x0; lanes stride the rows (M + 1 may exceed 32)
+    // rows 0..M-1 = draws, row M = x0.  A bulk copy costs its issuing thread ~45 ns, so the (M+1) x nchunks copies
+    // are dealt to all warps (row r -> warp r mod nwarps+1, chunk-major).
+    if (lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             const int c0 = c * chunk_vecs;
             const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
-            if (lane == 0) mbar_expect_tx(&s_bar[c], bytes * (uint32_t)(M + 1));
-            __syncwarp();
-            for (int r = lane; r <= M; r += 32) {
+            for (int r = warp; r <= M; r += nwarps + 1) {
                 const T* src = (r < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + r) * p.D + v_begin * VEC
                                        : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
                 tma_bulk_g2s(s_tile + (size_t)r * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
             }
         }
     }
+    __syncwarp();
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
     if (control) {

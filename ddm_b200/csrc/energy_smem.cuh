@@ -122,25 +122,30 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             for (int s = lane; s < P; s += 32) s_warp[w][s] = 0.f;
     }
     if (control && lane == 0) {
-        for (int c = 0; c < nchunks; ++c) mbar_init(&s_bar[c], 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the TMA (async proxy)
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_init(&s_bar[c], 1);
+            mbar_expect_tx(&s_bar[c], (uint32_t)min(chunk_vecs, nv - c * chunk_vecs) * 16u * (uint32_t)(M + 1));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the barriers visible to the TMA (async proxy)
     }
     __syncthreads();
     cudaGridDependencySynchronize();  // PDL: inputs may be produced by the previous kernel in the stream
     if (tid == 0) DDDM_TRACE(1);
-    if (control) {
-        const T* src = (lane < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + lane) * p.D + v_begin * VEC
-                                  : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
+    // One bulk copy costs its issuing thread ~45 ns (tools/trace_energy.py), so the (M+1) x nchunks copies are dealt
+    // to ALL warps (row r -> warp r mod nwarps+1, chunk-major): the tile is requested 5x sooner than from one warp.
+    if (lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             const int c0 = c * chunk_vecs;
             const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
-            if (lane == 0) mbar_expect_tx(&s_bar[c], bytes * (uint32_t)(M + 1));
-            __syncwarp();
-            if (lane <= M)
-                tma_bulk_g2s(s_tile + (size_t)lane * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
+            for (int r = warp; r <= M; r += nwarps + 1) {
+                const T* src = (r < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + r) * p.D + v_begin * VEC
+                                       : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
+                tma_bulk_g2s(s_tile + (size_t)r * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
+            }
         }
-        if (lane == 0) DDDM_TRACE(6);
+        if (control) DDDM_TRACE(6);
     }
+    __syncwarp();
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
     // gradient prefactors (independent of the distances: computed while the tile is in flight)
