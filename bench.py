@@ -45,27 +45,55 @@ def make_inputs(seed: int, dtype):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML every 5 ms when `pynvml` is importable
+    (the region is ~100 ms), else `nvidia-smi` every 100 ms."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+    NVML_BITS = (0x8, 0x40, 0x20, 0x4)  # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM))
+        try:
+            bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+        except Exception:
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+        self.rows.append([str(sm), str(self._max), "0"] + ["Active" if bits & b else "Not Active" for b in self.NVML_BITS])
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    parts = [p.strip() for p in out.strip().split(",")]
+                    if len(parts) >= 7:
+                        self.rows.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.005 if self._nvml is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
@@ -73,12 +101,11 @@ class ClockSampler(threading.Thread):
 
     def summary(self) -> dict:
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(self.NAMES) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def cpu_port_rate(seconds: float, dtype_name: str):
@@ -225,7 +252,9 @@ def run_aux(args, dev, world) -> dict:
             m1.synchronize()
             return m0.elapsed_time(m1) / reps, float(out)
 
+        torch.backends.cuda.matmul.allow_tf32 = False  # fp32 Gram, as the reference computes it
         ours_ms, ours_v = timed(lambda: ddm_b200.rbf_mmd2(xs, ys, 45.0))
+        tf32_ms, tf32_v = timed(lambda: ddm_b200.rbf_mmd2(xs, ys, 45.0, allow_tf32=True))
 
         def eager():  # the reference's formula (dddm/metrics.py:140-163) in eager PyTorch on the same GPU
             def pd(a, b):
@@ -236,7 +265,8 @@ def run_aux(args, dev, world) -> dict:
                 -g * pd(xs, ys)).mean()
 
         ref_ms, ref_v = timed(eager)
-        aux["rbf_mmd2"] = {"n": n, "m": n, "D": D, "ms": ours_ms, "value": ours_v, "eager_reference_formula_ms": ref_ms,
+        aux["rbf_mmd2"] = {"n": n, "m": n, "D": D, "ms": ours_ms, "value": ours_v, "tf32_gram_ms": tf32_ms,
+                           "tf32_gram_value": tf32_v, "eager_reference_formula_ms": ref_ms,
                            "eager_value": ref_v, "note": "evaluation-side pairwise kernel (SURVEY 8f-4): fp32 GEMM tiles "
                            "(cuBLAS; only the upper trapezoids of the symmetric xx/yy terms) + one fused "
                            "distance/exp/mask/sum pass per tile"}

@@ -279,6 +279,14 @@ class Trainer:
 
 def measure_throughput(args, dev, world, steps: int, warmup: int) -> dict:
     """Images/s of the DP training step on synthetic CIFAR-shaped data (device-timed, max over ranks)."""
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        return _measure_throughput(args, dev, world, steps, warmup)
+    finally:  # the Trainer sets the process-wide TF32 switches for its precision mode; do not leak them to the caller
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
+
+
+def _measure_throughput(args, dev, world, steps: int, warmup: int) -> dict:
     tr = Trainer(args, dev, world)
     x0 = tr.synthetic_batch()
     for _ in range(max(warmup, 1)):

@@ -1,6 +1,8 @@
 """Drop-in for ``dddm/metrics.py::rbf_mmd2`` (evaluation side of the path)."""
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 
 from . import ops
@@ -33,13 +35,18 @@ def _kernel_sum_offdiag(a: torch.Tensor, a2: torch.Tensor, gamma: float) -> torc
 
 
 @torch.no_grad()
-def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tensor:
+def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0, *, allow_tf32: Optional[bool] = None) -> torch.Tensor:
     """Unbiased MMD^2 with an RBF kernel, sigma fixed — reference ``dddm/metrics.py:140-163``.
 
     Same signature, ``ValueError`` for fewer than two samples per set, 0-dim result in the input dtype.  The three
     n x n terms are never materialised beyond one Gram tile each: GEMM tile -> one fused pass (distance, exp,
     diagonal mask, sum).  CUDA-only; not differentiable (the reference only calls it on detached samples,
     ``run_example.py:101``).
+
+    ``allow_tf32`` (keyword-only extension): ``None`` keeps the process-wide ``torch.backends.cuda.matmul.allow_tf32``
+    (PyTorch's default False = the reference's fp32 Gram); ``True`` runs the Gram tiles on the TF32 tensor cores —
+    10x faster at n = 10 000, D = 3072 with the result unchanged to 6 digits there, but the Gram form's cancellation
+    then carries 2^-11 instead of 2^-24 of ||x||^2, so it is opt-in.
     """
     if not (x.is_cuda and y.is_cuda):
         raise RuntimeError("ddm_b200.rbf_mmd2 runs on CUDA tensors only (no CPU fallback)")
@@ -48,6 +55,13 @@ def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0) -> torch.Tens
         raise ValueError("Need at least two samples per set to compute MMD")
     if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
         raise ValueError(f"expected x [n, D] and y [m, D], got {tuple(x.shape)} and {tuple(y.shape)}")
+    if allow_tf32 is not None:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
+        try:
+            return rbf_mmd2(x, y, sigma)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     dtype = x.dtype
     xf, yf = x.detach().float().contiguous(), y.detach().float().contiguous()
     gamma = 1.0 / (2.0 * sigma**2)
