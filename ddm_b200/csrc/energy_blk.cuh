@@ -1,4 +1,4 @@
-// energy_blk.cuh — TMA-staged, packed-fp32 energy-score kernel for m = 16 and m = 32 (BASELINE config 3).
+// energy_blk.cuh — TMA-staged, packed-fp32 energy-score kernel for m = 16, 24 and 32 (BASELINE config 3: 16, 32).
 //
 // Same skeleton as energy_smem.cuh (one cluster per minibatch row, CTAs split D, a control warp stages
 // the (m+1) x slab tile with chunked 1-D TMA bulk copies, 128 compute threads, PDL, fence-free row
@@ -40,7 +40,7 @@ template <typename T, int M, int MIN_CTAS>
 __global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
 energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
-    static_assert(M == 16 || M == 32, "blocked kernel: m in {16, 32} (diagonal blocks are swept in pairs)");
+    static_assert(M == 16 || M == 24 || M == 32, "blocked kernel: m in {16, 24, 32}");
     constexpr int P = M * (M + 1) / 2;
     constexpr int VEC = Elem<T>::kVec;
     constexpr int COLS = kBlkCols;
@@ -117,9 +117,9 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 acc2[i] = __ffma2_rn(d, d, acc2[i]);
             }
         }
-        float acc[M];
+        float acc[WarpReduce<M>::kPadded];
 #pragma unroll
-        for (int i = 0; i < M; ++i) acc[i] = acc2[i].x + acc2[i].y;
+        for (int i = 0; i < WarpReduce<M>::kPadded; ++i) acc[i] = (i < M) ? acc2[i < M ? i : 0].x + acc2[i < M ? i : 0].y : 0.f;
         WarpReduce<M>::run(acc, s_warp, lane);  // conf slot i == table-0 entry i
     }
     const float nb = (float)p.B * (float)M;
@@ -128,17 +128,21 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
 
     // ---- pass 1: block sweeps.  A work unit = (sweep, column split); units are dealt to the warps round-robin, the
     //      warp's lanes stride the unit's columns, so every distance of a split is produced by exactly one warp. ----
-    constexpr int NSWEEP = NB / 2 + NB * (NB - 1) / 2;  // M = 16: 2, M = 32: 8
-    const int nsplit = max(1, nwarps / NSWEEP);         // column splits (M = 16 with 4 warps: 2)
+    constexpr int NDIAG = (NB + 1) / 2;                  // diagonal blocks are swept two at a time
+    constexpr int NSWEEP = NDIAG + NB * (NB - 1) / 2;   // M = 16: 2, M = 24: 5, M = 32: 8
+    const int nsplit = (NSWEEP % nwarps == 0) ? 1 : kBlkMaxSplit;  // column splits: balance the units over the warps
     if (!control) {
         int waited = -1;  // chunks this thread has already waited for
         for (int unit = warp; unit < NSWEEP * nsplit; unit += nwarps) {
             const int sweep = unit / nsplit, split = unit - sweep * nsplit;
             const int q_begin = (int)((long)nq * split / nsplit), q_end = (int)((long)nq * (split + 1) / nsplit);
             float* table = s_warp + split * P;
-            if (sweep < NB / 2) {
-                // two diagonal blocks: 28 pair accumulators each
-                const int rA = 16 * sweep, rB = rA + 8;
+            if (sweep < NDIAG) {
+                // two diagonal blocks: 28 pair accumulators each (odd block count: the last sweep repeats its block
+                // in the second slot and drops that half of the result)
+                const int rA = 16 * sweep;
+                const bool single = rA + 8 >= M;
+                const int rB = single ? rA : rA + 8;
                 float2 acc2[56];
 #pragma unroll
                 for (int s = 0; s < 56; ++s) acc2[s] = make_float2(0.f, 0.f);
@@ -165,7 +169,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 for (int s = 0; s < WRD::kPadded; ++s) acc[s] = (s < 56) ? acc2[s < 56 ? s : 0].x + acc2[s < 56 ? s : 0].y : 0.f;
                 WRD::run(acc, s_tmp[warp], lane);
                 __syncwarp();
-                for (int l = lane; l < 56; l += 32) {
+                for (int l = lane; l < (single ? 28 : 56); l += 32) {
                     const int blk = l / 28, r0 = blk ? rB : rA;
                     int i, j;
                     unpair8(l - 28 * blk, i, j);
@@ -174,7 +178,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 __syncwarp();
             } else {
                 // off-diagonal 8x8 block (bi < bj), enumerated row-major
-                int k = sweep - NB / 2, bi = 0;
+                int k = sweep - NDIAG, bi = 0;
                 while (k >= NB - 1 - bi) {
                     k -= NB - 1 - bi;
                     ++bi;

@@ -7,7 +7,7 @@ SmemPlan plan_blk(int m, int D, int elem_size, bool aligned16) {
     SmemPlan s{};
     s.ok = false;
     const int vecw = 16 / elem_size;
-    if (!(m == 16 || m == 32) || D < 1 || !aligned16 || D % vecw != 0) return s;
+    if (!(m == 16 || m == 24 || m == 32) || D < 1 || !aligned16 || D % vecw != 0) return s;
     const long nvec = D / vecw;
     const int P = m * (m + 1) / 2;
     const Tuning& t = tuning();

@@ -25,6 +25,7 @@ template <typename T>
 int launch_energy_blk_any(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
     switch (p.m) {
         case 16: return launch_energy_blk_m<T, 16>(p, plan, stream);
+        case 24: return launch_energy_blk_m<T, 24>(p, plan, stream);
         case 32: return launch_energy_blk_m<T, 32>(p, plan, stream);
         default: return DDDM_ERR_UNSUPPORTED;
     }

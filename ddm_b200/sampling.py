@@ -66,9 +66,12 @@ _graph_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # model
 def _sample_graphed(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, eps_churn: float) -> torch.Tensor:
     """Replays a cached one-step graph (captured on first use for this model / batch shape / churn: capture costs
     ~1 s, a replayed step ~1 ms).  The graph reads the model's parameters in place, so in-place weight updates are
-    picked up; re-allocating parameters (``model.to(other_dtype)``) needs a new model object or ``clear_graph_cache``."""
+    picked up; if parameters are re-allocated (``model.to(other_dtype)``) the key changes and a new graph is captured."""
     dev, B = x.device, x.shape[0]
-    key = (tuple(x.shape), x.dtype, float(eps_churn), str(dev))
+    # the graph bakes in the addresses of the model's parameters and buffers: re-capture if any of them moved
+    # (model.to(other dtype/device), load_state_dict(assign=True), ...)
+    storage = hash(tuple(t.data_ptr() for t in list(model.parameters()) + list(model.buffers())))
+    key = (tuple(x.shape), x.dtype, float(eps_churn), str(dev), storage, model.training)
     per_model = _graph_cache.setdefault(model, {})
     st = per_model.get(key)
     if st is None:

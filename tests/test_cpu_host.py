@@ -67,8 +67,9 @@ def test_kernel_plans(cabi):
         cabi.set_tuning("energy.variant", 0)
         assert cabi.describe_energy(128, 32, 3072).startswith("blk<f32,M=32> tma-bulk")
         assert cabi.describe_energy(128, 16, 3072, "bf16").startswith("blk<bf16,M=16> tma-bulk")
-        assert cabi.describe_energy(128, 24, 3072).startswith("tile<f32,m=24>") and "tma-bulk" in cabi.describe_energy(
-            128, 24, 3072)
+        assert cabi.describe_energy(128, 24, 3072).startswith("blk<f32,M=24> tma-bulk")
+        assert cabi.describe_energy(128, 20, 3072).startswith("tile<f32,m=20>") and "tma-bulk" in cabi.describe_energy(
+            128, 20, 3072)
         assert "ldg" in cabi.describe_energy(4, 16, 7)
         assert cabi.describe_energy(4, 65, 8) == "unsupported"
         cabi.set_tuning("energy.variant", 2)

@@ -213,7 +213,7 @@ def test_kernel_variants_agree(dev):
     assert len(seen) >= 12, seen
 
 
-@pytest.mark.parametrize("m", [16, 32])
+@pytest.mark.parametrize("m", [16, 24, 32])
 def test_blocked_kernel_plans_agree(dev, m):
     """m = 16 / 32: the blocked packed-fp32 kernel (variant 4) under every cluster size and thread count, and the
     generic chunked tile kernel (variant 2), against the oracle — fp32 and bf16, early and late regime, all betas."""

@@ -365,3 +365,26 @@ def test_sampler_cuda_graph_equals_eager(dev):
         tail = torch.randn(4, device=dev)  # the generator must end at the same position
         outs.append(tail)
     assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+
+
+def test_sampler_graph_cache_follows_parameter_storage(dev):
+    """A cached sampler graph must not outlive the parameter storage it captured (model.to(dtype) re-allocates)."""
+    import ddm_b200
+    from ddm_b200 import sampling
+
+    model = MixModel().to(dev)
+    torch.manual_seed(7)
+    a = ddm_b200.sample_dddm(model, n_samples=16, steps=3, device=str(dev), data_shape=(4,), cuda_graph=True)
+    n_graphs = len(sampling._graph_cache[model])
+    with torch.no_grad():
+        model.a.mul_(0.5)  # in-place update: same storage, same graph, new values
+    torch.manual_seed(7)
+    b = ddm_b200.sample_dddm(model, n_samples=16, steps=3, device=str(dev), data_shape=(4,), cuda_graph=True)
+    assert len(sampling._graph_cache[model]) == n_graphs and not torch.equal(a, b)
+    torch.manual_seed(7)
+    ref = ddm_b200.sample_dddm(model, n_samples=16, steps=3, device=str(dev), data_shape=(4,))
+    assert torch.equal(b, ref)
+    model.double().float()  # re-allocates every parameter
+    torch.manual_seed(7)
+    c = ddm_b200.sample_dddm(model, n_samples=16, steps=3, device=str(dev), data_shape=(4,), cuda_graph=True)
+    assert len(sampling._graph_cache[model]) == n_graphs + 1 and torch.equal(c, ref)
