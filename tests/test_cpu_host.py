@@ -172,3 +172,27 @@ def test_patch_reference_rebinds_imported_names():
     finally:
         for k in [k for k in sys.modules if k.startswith("fake_dddm")]:
             del sys.modules[k]
+
+
+def test_sass_shows_tma_bulk_copies_and_packed_fp32():
+    """What the built library actually contains (B200_PROFILING.md, 'What proves a Blackwell-native kernel'):
+    the energy kernels stage their tiles with TMA bulk copies (SASS UBLKCP, completion on mbarriers: SYNCS) and do
+    their arithmetic in packed fp32 (FFMA2 / FADD2); no legacy tensor-core path (HMMA) is linked in."""
+    import shutil
+    import subprocess
+
+    from ddm_b200 import _cabi
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump) or not os.path.exists(_cabi.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run([cuobjdump, "-sass", _cabi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass
+    per_kernel = sass.split("Function : ")
+    smem = [k for k in per_kernel if "energy_fused_smem_kernelIfLi8" in k.split("\n", 1)[0]]
+    blk = [k for k in per_kernel if "energy_fused_blk_kernelIfLi32" in k.split("\n", 1)[0]]
+    assert smem and blk
+    for k in smem + blk:
+        assert "UBLKCP" in k and "SYNCS" in k, "TMA bulk copy + mbarrier expected"
+        assert k.count("FFMA2") > 100 and k.count("FADD2") > 100, "packed fp32 arithmetic expected"
+    assert "HMMA" not in sass and "HGMMA" not in sass
