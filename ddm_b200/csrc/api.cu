@@ -242,6 +242,7 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.pdl")) t.pdl = value;
     else if (!strcmp(key, "energy.threads")) t.threads = value;
     else if (!strcmp(key, "energy.ctas")) t.ctas = value;
+    else if (!strcmp(key, "energy.cols")) t.cols = value;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -254,6 +255,7 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.pdl")) return t.pdl;
     if (!strcmp(key, "energy.threads")) return t.threads;
     if (!strcmp(key, "energy.ctas")) return t.ctas;
+    if (!strcmp(key, "energy.cols")) return t.cols;
     return DDDM_ERR_BAD_ARGUMENT;
 }
 int dddm_set_trace_buffer(void* device_buffer) {

@@ -22,6 +22,7 @@ struct Tuning {
     int threads = 0;  // threads per CTA for variant 3 (0 = auto)
     int pdl = 1;      // programmatic dependent launch (the prologue overlaps the previous kernel's tail; every
                       // kernel waits on cudaGridDependencySynchronize() before touching global memory)
+    int cols = 0;     // experiment: columns per thread step of the bf16 variant-3 kernel (0 = default)
     int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
     void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)
 };

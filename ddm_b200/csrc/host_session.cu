@@ -143,8 +143,9 @@ int dddm_session_enqueue_host(dddm_session* s, const void* xhat_host, const void
     SESSION_TRY(cudaMemcpyAsync(out_host, k.out, 4 * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
     if (grad_host) SESSION_TRY(cudaMemcpyAsync(grad_host, k.grad, nx, cudaMemcpyDeviceToHost, s->s_out));
     SESSION_TRY(cudaEventRecord(k.downloaded, s->s_out));
-    // the next upload into this slot must not overtake this step's kernels
-    SESSION_TRY(cudaStreamWaitEvent(s->s_in, k.computed, 0));
+    // No device-side edge from this step's kernels back to the upload stream: the next upload into THIS slot is three
+    // steps away and is preceded by the host-side wait on `downloaded` above (download follows compute), while the
+    // next step's upload goes to another slot and may overlap these kernels.
     k.busy = true;
     return DDDM_OK;
 }
