@@ -306,7 +306,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets (0 = enough to exceed 8x L2)")
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=6,
                     help="streams the independent steps are issued on round-robin inside the CUDA graph (1 = serialized)")
     ap.add_argument("--tune", default="", help="comma list key=value for dddm_set_tuning, e.g. energy.cluster=4")
     ap.add_argument("--dit-steps", type=int, default=10,
