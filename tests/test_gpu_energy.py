@@ -327,3 +327,25 @@ def test_errors_are_loud(dev):
                              torch.zeros(2, 2, device=dev, dtype=torch.float64), 1.0)
     with pytest.raises(ValueError):
         ops.energy_terms_fwd(torch.zeros(2, 2, 3, device=dev), torch.zeros(2, 2, device=dev), 1.0)
+
+
+@pytest.mark.parametrize("m,D,B", [(8, 3072, 1500), (4, 768, 5000), (16, 1024, 700), (8, 2, 20000)])
+def test_many_rows_multi_wave(dev, m, D, B):
+    """More rows than resident CTAs (several waves of the grid, last-arriver reduction over thousands of rows):
+    the batch means must equal the mean of per-slice means, the gradient of a slice must equal the slice's own
+    gradient scaled by its share of the batch, and a sample of rows is checked against the oracle."""
+    xh, x0 = _synthetic(B, m, D, "late", seed=B + m)
+    xh, x0 = xh.to(dev), x0.to(dev)
+    out, g = _fused(xh, x0, 0.6, 0.1, 1.0)
+    cuts = [0, B // 3, B // 3 + 77, B]
+    conf = inter = 0.0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        o, gs = _fused(xh[a:b].contiguous(), x0[a:b].contiguous(), 0.6, 0.1, 1.0)
+        conf += o[1] * (b - a) / B
+        inter += o[2] * (b - a) / B
+        assert _rel(g[a:b], gs * (b - a) / B) <= 2e-6
+    assert abs(conf - out[1]) <= 2e-6 * abs(out[1]) and abs(inter - out[2]) <= 2e-6 * abs(out[2])
+    rows = np.linspace(0, B - 1, 9).astype(int)
+    sub_h, sub_0 = xh[rows].double().cpu().numpy(), x0[rows].double().cpu().numpy()
+    _, _, _, gref = oracle.energy_loss(sub_h, sub_0, 0.1, 1.0, 0.6)
+    assert _rel(g[rows], gref * len(rows) / B) <= FP32_REL
