@@ -159,6 +159,16 @@ static int energy_terms_bwd(const T* xhat, const T* x0, const float* dist, const
     p.mode = kModeTerms;
     const bool al = is_aligned16(xhat) && is_aligned16(x0) && is_aligned16(grad_xhat) &&
                     (!grad_x0 || is_aligned16(grad_x0)) && ((long)D * (long)sizeof(T)) % 16 == 0;
+    if (tuning().variant == 0 || tuning().variant == 3) {
+        // TMA-staged packed-fp32 kernel in backward mode (pass 2 only, coefficients from the saved distances)
+        SmemPlan sp = plan_smem(m, D, (int)sizeof(T), al);
+        if (sp.ok) {
+            p.mode = kModeBwd;
+            p.trace = static_cast<unsigned long long*>(tuning().trace);
+            return launch_energy_smem<T>(p, sp, stream);
+        }
+        if (tuning().variant == 3) return DDDM_ERR_UNSUPPORTED;
+    }
     if (tuning().variant != 2) {
         RegPlan plan = plan_reg(m, D, (int)sizeof(T), al, true);
         if (plan.ok) return launch_energy_bwd_reg<T>(p, plan, stream);

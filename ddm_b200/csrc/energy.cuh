@@ -9,6 +9,7 @@ namespace dddm {
 enum EnergyMode : int {
     kModeLoss = 0,   // training.py:84-85: out = {loss, conf, inter, W}; grad (optional) = dloss/dxhat
     kModeTerms = 1,  // losses.py:5-25:    out = {conf, inter}; dist saved for the backward
+    kModeBwd = 2,    // backward of kModeTerms from the saved distances: grad_xhat (+ grad_x0), no pass 1, no row sums
 };
 
 struct EnergyParams {

@@ -102,8 +102,9 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x >> 5) - 1;
     const int nthr = nwarps * 32;
     const bool control = warp == nwarps;
-    const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : (int)blockIdx.x;
     const int b = blockIdx.y;
+    const bool bwd = p.mode == kModeBwd;  // launched without a cluster: the D-slabs of a row are independent CTAs
     if (tid == 0) DDDM_TRACE(0);
     if (cluster_size > 1) cluster_arrive_relaxed();  // phase 0: "my shared memory exists"
 
@@ -148,16 +149,18 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     __syncwarp();
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
-    // gradient prefactors (independent of the distances: computed while the tile is in flight)
+    // gradient prefactors (independent of the distances: computed while the tile is in flight);
+    // kModeBwd: upstream gradients of conf / inter are device scalars (SURVEY.md §8a closed form)
     const float nb = (float)p.B * (float)M;
-    const float pre_conf = 2.0f * W / nb;
-    const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
+    const float pre_conf = bwd ? 2.0f * p.g_conf[0] / nb : 2.0f * W / nb;
+    const float pre_pair = bwd ? 4.0f * p.g_inter[0] / (nb * (float)(M - 1))
+                               : -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
     // ---- pass 1: squared distances, COLS columns per thread per step ----
     float2 acc2[P];
 #pragma unroll
     for (int s = 0; s < P; ++s) acc2[s] = make_float2(0.f, 0.f);
-    for (int q = control ? nq : tid; q < nq; q += nthr) {
+    for (int q = (control || bwd) ? nq : tid; q < nq; q += nthr) {
         if ((q - tid) % chunk_q == 0) {  // warp-uniform: entering a new chunk
             mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
             if (tid == 0 && q == 0) DDDM_TRACE(2);
@@ -186,7 +189,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     float acc[WR::kPadded];
 #pragma unroll
     for (int s = 0; s < WR::kPadded; ++s) acc[s] = (s < P) ? acc2[s < P ? s : 0].x + acc2[s < P ? s : 0].y : 0.f;
-    if (!control) WR::run(acc, s_warp[warp], lane);
+    if (!control && !bwd) WR::run(acc, s_warp[warp], lane);
     if (tid == 0) DDDM_TRACE(8);
     __syncthreads();
     if (tid == 0) DDDM_TRACE(9);
@@ -206,7 +209,9 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     if (tid < P) {
         const int s = tid;
         float total = 0.f;
-        if (cluster_size > 1) {
+        if (bwd) {
+            total = p.dist[(long)b * P + s];
+        } else if (cluster_size > 1) {
             for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][s];
         } else {
             total = (s_warp[0][s] + s_warp[1][s]) + (s_warp[2][s] + s_warp[3][s]);
@@ -215,7 +220,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         pow_value_deriv(total, p.pw, val, der);
         s_val[s] = val;
         s_coef[s] = ((s < M) ? pre_conf : pre_pair) * der;
-        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
+        if (!bwd && p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
     }
     if (tid == 0) DDDM_TRACE(10);
     __syncthreads();
@@ -223,7 +228,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
 
     // ---- cross-row reduction: the control warp of the row's first CTA, concurrently with pass 2 ----
     if (control) {
-        if (rank == 0) {
+        if (rank == 0 && !bwd) {
             // conf = sum of slots [0, M), inter = 2 * sum of slots [M, P) (ordered pairs), fixed-shape tree
             float c = (lane < M) ? s_val[lane] : 0.f;
             float it = (lane >= M && lane < P) ? s_val[lane] : 0.f;
@@ -247,7 +252,9 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             K2[s] = make_float2(k, k);
         }
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
+        T* __restrict__ g0row = (p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
         for (int q = tid; q < nq; q += nthr) {
+            if (bwd && (q - tid) % chunk_q == 0) mbar_wait(&s_bar[(q - tid) / chunk_q], 0);  // no pass 1 waited for it
             float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
             for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
@@ -255,6 +262,12 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             for (int h = 0; h < NP; ++h) {
 #pragma unroll
                 for (int i = 0; i < M; ++i) g[i][h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
+                if (g0row != nullptr) {  // d/dx0 of the confinement term: -sum_i k_i (x_i - x0), fixed order
+                    float2 s0 = g[0][h];
+#pragma unroll
+                    for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][h]);
+                    x[M][h] = make_float2(-s0.x, -s0.y);  // x0 is not needed below: reuse its registers
+                }
 #pragma unroll
                 for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -267,6 +280,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             }
 #pragma unroll
             for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+            if (g0row != nullptr) stg_step<T, COLS>(g0row + (long)q * COLS, x[M]);
         }
     }
     if (tid == 0) DDDM_TRACE(5);

@@ -30,8 +30,10 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
         if (e != cudaSuccess) return (int)e;
         conf = plan.smem_bytes;
     }
-    return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
-                             p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);
+    // the backward needs no cross-CTA sum: same grid, but the D-slabs of a row run as independent CTAs
+    const int cluster = (p.mode == kModeBwd) ? 1 : plan.cluster;
+    return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, cluster, stream,
+                             p, plan.slab_vecs, cluster, plan.chunk_vecs);
 }
 
 #define DDDM_DISPATCH_M_SMEM(T, p, plan, stream)                         \
