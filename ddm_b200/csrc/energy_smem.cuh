@@ -82,7 +82,7 @@ __host__ __device__ constexpr int pair_slot(int i, int j) {  // i < j
         if (p.trace != nullptr) p.trace[((long)b * cluster_size + rank) * 16 + (slot)] = globaltimer_ns(); \
     } while (0)
 
-template <typename T, int M, int COLS, int MIN_CTAS>
+template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false>
 __global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
 energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
@@ -104,7 +104,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     const bool control = warp == nwarps;
     const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : (int)blockIdx.x;
     const int b = blockIdx.y;
-    const bool bwd = p.mode == kModeBwd;  // launched without a cluster: the D-slabs of a row are independent CTAs
+    constexpr bool bwd = BWD;  // kModeBwd, its own instantiation; launched without a cluster (independent D-slabs)
     if (tid == 0) DDDM_TRACE(0);
     if (cluster_size > 1) cluster_arrive_relaxed();  // phase 0: "my shared memory exists"
 

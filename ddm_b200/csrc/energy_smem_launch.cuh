@@ -14,8 +14,13 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
     constexpr int kMinCtas = (sizeof(T) == 4) ? 2 : 3;
     auto kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas>;
     int which = 0;
+    if (p.mode == kModeBwd) {
+        kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas, true>;
+        which = 3;
+    }
     if constexpr (sizeof(T) == 2) {
-        if (tuning().ctas == 4) {  // experiment: 2-column steps under the 4-CTA register cap (96 registers, small spills)
+        if (p.mode == kModeBwd) {
+        } else if (tuning().ctas == 4) {  // experiment: 2-column steps under the 4-CTA register cap (96 registers, small spills)
             kernel = energy_fused_smem_kernel<T, M, 2, 4>;
             which = 1;
         } else if (tuning().cols == 2) {  // experiment: 2-column steps under the 3-CTA register cap
@@ -23,7 +28,7 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
             which = 2;
         }
     }
-    static size_t configured[3] = {0, 0, 0};
+    static size_t configured[4] = {0, 0, 0, 0};
     size_t& conf = configured[which];
     if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
