@@ -388,3 +388,17 @@ def test_sampler_graph_cache_follows_parameter_storage(dev):
     torch.manual_seed(7)
     c = ddm_b200.sample_dddm(model, n_samples=16, steps=3, device=str(dev), data_shape=(4,), cuda_graph=True)
     assert len(sampling._graph_cache[model]) == n_graphs + 1 and torch.equal(c, ref)
+
+
+def test_toy_gmm_trains_end_to_end(dev):
+    """BASELINE config 1 (2-D bimodal GMM, DDDMMLP, batch 512, m=8, beta=0.1, Adam 2e-3, 20 sampling steps) through the
+    kernels.  The reference's own flow run on CPU for the same 1500 steps gives MMD^2(sigma=1) = 0.043 / 0.26 / 0.30 /
+    0.23 for seeds 42 / 1 / 2 / 3 (from 1.33 untrained; run_example.py trains 5000-10000 steps): the kernels must land
+    in the same range, on both modes."""
+    from tools.toy_gmm_e2e import run
+
+    r = run(steps=1500, seed=42, dev=str(dev), log_every=1500)
+    assert r["mmd2_untrained"] > 1.0 and r["mmd2_rbf_sigma1"] < 0.45, r
+    assert 0.3 < r["fraction_left_mode"] < 0.7 and r["fraction_within_3sigma_of_a_mode"] > 0.6, r
+    h = r["history"][-1]
+    assert 0.35 < h["loss"] < 0.55 and 0.85 < h["confidence"] < 1.05 and 0.75 < h["interaction"] < 0.95, h
