@@ -227,6 +227,36 @@ def run_aux(args, dev, world) -> dict:
         aux["dit_train"] = launcher.measure_throughput(targs, dev, world, steps=args.dit_steps, warmup=3)
         aux["dit_train"]["config"] = ("DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
                                       "data-parallel (one flat-gradient NCCL all-reduce), loss kernels K4+K2c+K1")
+    if args.dit_steps > 0 and world == 1 and args.cpu_seconds > 0:
+        # CPU baseline of config 4 at a REDUCED batch (a full B=128 CPU step is ~5.7 TFLOP): the
+        # reference's step (oracle/torch_port.training_step = dddm/training.py:57-85) + backward + clip + AdamW on the
+        # host cores, default DiT in fp32, B=4, m=8.  Reported beside the GPU figure, never on the product path.
+        from ddm_b200 import backbones
+        from oracle import torch_port
+
+        cb, cm = 4, 8
+        torch.manual_seed(0)
+        cpu_model = backbones.DDDMDiT()
+        cpu_opt = torch.optim.AdamW(cpu_model.parameters(), lr=1e-4, weight_decay=0.01)
+        cx0 = torch.rand(cb, 3, 32, 32) * 2 - 1
+
+        def cpu_step():
+            t, eps, xi = torch.rand(cb), torch.randn_like(cx0), torch.randn(cb, cm, 3, 32, 32)
+            loss = torch_port.training_step(cpu_model, cx0, t, eps, xi, m=cm, beta=BETA, lam=LAM, w_bias=W_BIAS)[0]
+            cpu_opt.zero_grad(set_to_none=True)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(cpu_model.parameters(), 1.0)
+            cpu_opt.step()
+
+        cpu_step()
+        c0 = time.perf_counter()
+        nsteps = 3
+        for _ in range(nsteps):
+            cpu_step()
+        cdt = (time.perf_counter() - c0) / nsteps
+        aux["dit_train"]["cpu_baseline"] = {"img_per_s": cb / cdt, "s_per_step": cdt, "batch": cb, "m": cm, "kind": "port",
+                                            "cores": torch.get_num_threads(),
+                                            "sample": f"{nsteps} steps at the reduced batch {cb} (fp32, eager PyTorch)"}
     if args.sampler_samples > 0:
         from ddm_b200.backbones import DDDMDiT
         from ddm_b200.sampling import sample_dddm
@@ -298,7 +328,7 @@ def run_aux(args, dev, world) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])

@@ -252,7 +252,8 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             K2[s] = make_float2(k, k);
         }
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
-        T* __restrict__ g0row = (p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
+        // grad_x0 exists only in the backward instantiation (the fused loss never differentiates w.r.t. the data)
+        T* __restrict__ g0row = (BWD && p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
         for (int q = tid; q < nq; q += nthr) {
             if (bwd && (q - tid) % chunk_q == 0) mbar_wait(&s_bar[(q - tid) / chunk_q], 0);  // no pass 1 waited for it
             float2 x[M + 1][NP], g[M][NP];
@@ -262,7 +263,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             for (int h = 0; h < NP; ++h) {
 #pragma unroll
                 for (int i = 0; i < M; ++i) g[i][h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
-                if (g0row != nullptr) {  // d/dx0 of the confinement term: -sum_i k_i (x_i - x0), fixed order
+                if (BWD && g0row != nullptr) {  // d/dx0 of the confinement term: -sum_i k_i (x_i - x0), fixed order
                     float2 s0 = g[0][h];
 #pragma unroll
                     for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][h]);
@@ -280,7 +281,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             }
 #pragma unroll
             for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
-            if (g0row != nullptr) stg_step<T, COLS>(g0row + (long)q * COLS, x[M]);
+            if (BWD && g0row != nullptr) stg_step<T, COLS>(g0row + (long)q * COLS, x[M]);
         }
     }
     if (tid == 0) DDDM_TRACE(5);
