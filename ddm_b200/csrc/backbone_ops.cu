@@ -287,7 +287,7 @@ static int ln_bwd(const T* dy, const T* x, const float* mean, const float* rstd,
     if (N < 1 || C < 4 || C % 4 != 0 || C > 32 * 4 * kLnMaxVec) return DDDM_ERR_UNSUPPORTED;
     if (!al16(x) || !al16(dy) || !al16(dx) || !al16(gamma) || ((long)C * (long)sizeof(T)) % 16 != 0) return DDDM_ERR_BAD_ALIGNMENT;
     const long want = (N + kLnWarps - 1) / kLnWarps;
-    int grid = (int)(want < (long)sms() * 2 ? want : (long)sms() * 2);
+    int grid = (int)(want < (long)sms() * 4 ? want : (long)sms() * 4);  // 4 CTAs x 8 warps per SM: enough rows in flight
     const size_t per = (size_t)2 * C * sizeof(float);
     if (part_bytes < per) return DDDM_ERR_BAD_ARGUMENT;
     if ((size_t)grid * per > part_bytes) grid = (int)(part_bytes / per);
