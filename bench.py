@@ -188,6 +188,8 @@ def run_reference(args) -> None:
 
     from oracle import torch_port
 
+    # torchrun exports OMP_NUM_THREADS=1 for N > 1: the reference arm uses every host core it is allowed to
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     xh, x0, t = make_inputs(0, torch.float32)
     w = torch_port.sigmoid_weight(t, W_BIAS).mean()
     # bounded: each step is ~0.1-0.3 s of CPU work; cap the whole run at a few minutes
