@@ -108,6 +108,27 @@ def clear_graph_cache() -> None:
     _graph_cache.clear()
 
 
+def sample_dddm_chunked(model, n_samples: int, steps: int = 20, eps_churn: float = 1.0, device: str = "cuda",
+                        data_shape=None, *, chunk: int = 4096, cuda_graph: bool = True, out_device=None) -> torch.Tensor:
+    """Algorithm 2 for evaluation-sized sample counts (``eval_samples: 50000``, configs/cifar10_dit.yaml:32;
+    ``train_cifar10_dit.py:325-335`` samples them in one call): ``n_samples`` drawn ``chunk`` at a time so that the
+    backbone's activations stay bounded, every full chunk replaying ONE cached CUDA graph.  Chunks are concatenated on
+    ``out_device`` (default: the sampling device).  Same per-chunk RNG order as :func:`sample_dddm`."""
+    if n_samples < 0 or chunk < 1:
+        raise ValueError("n_samples must be >= 0 and chunk >= 1")
+    parts = []
+    done = 0
+    while done < n_samples:
+        n = min(chunk, n_samples - done)
+        x = sample_dddm(model, n, steps, eps_churn, device=device, data_shape=data_shape, cuda_graph=cuda_graph)
+        parts.append(x if out_device is None else x.to(out_device))
+        done += n
+    if not parts:
+        shape = (2,) if data_shape is None else tuple(data_shape)
+        return torch.empty((0, *shape), device=out_device or device)
+    return torch.cat(parts, dim=0)
+
+
 def sample_dddm_sharded(model, n_samples: int, steps: int = 20, eps_churn: float = 1.0, data_shape=None, *,
                         group=None, gather: bool = True, seed: Optional[int] = None,
                         cuda_graph: bool = False) -> torch.Tensor:

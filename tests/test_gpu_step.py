@@ -402,3 +402,19 @@ def test_toy_gmm_trains_end_to_end(dev):
     assert 0.3 < r["fraction_left_mode"] < 0.7 and r["fraction_within_3sigma_of_a_mode"] > 0.6, r
     h = r["history"][-1]
     assert 0.35 < h["loss"] < 0.55 and 0.85 < h["confidence"] < 1.05 and 0.75 < h["interaction"] < 0.95, h
+
+
+def test_chunked_sampler_equals_per_chunk_calls(dev):
+    """sample_dddm_chunked (evaluation-sized sample counts) == the concatenation of sample_dddm calls on the same RNG
+    stream, ragged last chunk included; the full chunks share one cached graph."""
+    import ddm_b200
+    from ddm_b200 import sampling
+
+    model = MixModel().to(dev)
+    torch.manual_seed(5)
+    got = ddm_b200.sample_dddm_chunked(model, 70, steps=4, device=str(dev), data_shape=(3, 4, 4), chunk=32)
+    torch.manual_seed(5)
+    want = torch.cat([ddm_b200.sample_dddm(model, n, steps=4, device=str(dev), data_shape=(3, 4, 4)) for n in (32, 32, 6)])
+    assert got.shape == (70, 3, 4, 4) and torch.equal(got, want)
+    assert len(sampling._graph_cache[model]) == 2  # one graph for the 32-sample chunks, one for the ragged tail
+    assert ddm_b200.sample_dddm_chunked(model, 0, steps=2, device=str(dev), data_shape=(2,)).shape == (0, 2)
