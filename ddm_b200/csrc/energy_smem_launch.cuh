@@ -20,8 +20,8 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
     }
     if constexpr (sizeof(T) == 2) {
         if (p.mode == kModeBwd) {
-        } else if (tuning().ctas == 4) {  // experiment: 2-column steps under the 4-CTA register cap (96 registers, small spills)
-            kernel = energy_fused_smem_kernel<T, M, 2, 4>;
+        } else if (tuning().ctas == 4) {  // experiment: the 4-CTA register cap (96 registers, ~170 B of spills)
+            kernel = energy_fused_smem_kernel<T, M, 4, 4>;
             which = 1;
         } else if (tuning().cols == 2) {  // experiment: 2-column steps under the 3-CTA register cap
             kernel = energy_fused_smem_kernel<T, M, 2, 3>;
