@@ -228,11 +228,30 @@ class Trainer:
         self._update()
         return packed
 
+    def _snapshot(self):
+        state = {k: {n: (v.clone() if torch.is_tensor(v) else v) for n, v in st.items()} for k, st in self.opt.state.items()}
+        return self.flat_master.clone(), state, torch.cuda.get_rng_state(self.dev)
+
+    def _restore(self, snap) -> None:
+        """Undo the warm-up steps: they exist to build library plans, allocator pools, optimizer state tensors and NCCL
+        communicators before the capture, not to train."""
+        master, state, rng = snap
+        self.flat_master.copy_(master)
+        if self.bf16:
+            self.flat_shadow.copy_(self.flat_master)
+        for k, st in self.opt.state.items():
+            for n, v in st.items():
+                if torch.is_tensor(v):
+                    old = state.get(k, {}).get(n)
+                    v.copy_(old) if old is not None else v.zero_()  # no earlier state: fresh = zeros, step 0
+        torch.cuda.set_rng_state(rng, self.dev)
+
     def _capture(self, x0: torch.Tensor) -> None:
         self._static_x0 = x0.clone()
         self._static_t = torch.zeros(x0.shape[0], device=self.dev, dtype=x0.dtype)
         self._static_wsum = torch.zeros(1, device=self.dev)
         eager = self._split_step_eager if self.split_graph else self._step_impl
+        snap = self._snapshot()
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
@@ -240,6 +259,7 @@ class Trainer:
                 eager(self._static_x0)
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
+        self._restore(snap)
         self._graph = torch.cuda.CUDAGraph()
         if not self.split_graph:
             with torch.cuda.graph(self._graph):

@@ -418,3 +418,36 @@ def test_chunked_sampler_equals_per_chunk_calls(dev):
     assert got.shape == (70, 3, 4, 4) and torch.equal(got, want)
     assert len(sampling._graph_cache[model]) == 2  # one graph for the 32-sample chunks, one for the ragged tail
     assert ddm_b200.sample_dddm_chunked(model, 0, steps=2, device=str(dev), data_shape=(2,)).shape == (0, 2)
+
+
+def test_trainer_cuda_graph_equals_eager(dev, monkeypatch):
+    """launcher.Trainer: the whole-step CUDA graph (one GPU) and the two-graph form used with several ranks give the
+    same parameters as the eager step after a few optimisation steps from the same seed — the warm-up steps of the
+    capture are rolled back (weights, optimizer state, RNG position).  The very first bf16 run of a process picks
+    its cuBLAS kernels cold and differs from every later run by rounding, so a throw-away eager run comes first."""
+    from ddm_b200 import launcher
+
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    base = ["--synthetic", "--depth", "2", "--embed-dim", "96", "--heads", "3", "--batch", "8", "--m", "4", "--lr", "1e-3"]
+    try:
+        for precision, tol in (("bf16", 1e-3), ("fp32", 1e-4)):
+            results = {}
+            for mode in ("warmup", "eager", "graph", "split"):
+                monkeypatch.setenv("DDDM_SPLIT_GRAPH", "1" if mode == "split" else "0")
+                args = launcher.build_parser().parse_args(base + ["--precision", precision] +
+                                                          (["--cuda-graph"] if mode in ("graph", "split") else ["--no-cuda-graph"]))
+                tr = launcher.Trainer(args, dev, 1)
+                assert tr.use_graph == (mode in ("graph", "split")) and tr.split_graph == (mode == "split")
+                start = tr.flat_master.clone()
+                losses = [tr.step(tr.synthetic_batch())["loss"] for _ in range(4)]
+                results[mode] = (tr.flat_master - start, losses, torch.rand(3, device=dev))
+            ref_d, ref_l, ref_r = results["eager"]
+            assert float(ref_d.abs().max()) > 1e-3  # the optimizer moved the weights
+            for mode in ("graph", "split"):
+                d, l, r = results[mode]
+                assert torch.equal(r, ref_r), (precision, mode, "RNG position differs")
+                assert max(abs(a - b) for a, b in zip(l, ref_l)) <= 1e-5 * max(abs(b) for b in ref_l), (precision, mode, l, ref_l)
+                rel = float((d - ref_d).norm() / ref_d.norm())
+                assert rel <= tol, (precision, mode, rel)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
