@@ -201,3 +201,28 @@ def test_rbf_mmd2_oracle_matches_reference(golden_mmd):
         assert abs(float(g[f"{n}/mmd2_f32"]) - mmd2) <= 2e-6 * max(kxx, kyy, kxy, 1e-30) + 1e-30, n
     with pytest.raises(ValueError):
         oracle.rbf_mmd2(np.zeros((1, 2)), np.zeros((3, 2)))
+
+
+def test_oracle_gradient_is_the_derivative_of_the_oracle_loss():
+    """The C oracle's closed-form gradient against central finite differences of its own loss, and the
+    invariances the GPU property tests rely on (common translation, permutation of the draws, permutation of D)."""
+    rng = np.random.default_rng(0)
+    for (B, m, D, beta) in ((2, 3, 5, 0.1), (1, 4, 7, 1.0), (2, 2, 3, 1.7), (1, 5, 4, 2.0)):
+        x0 = rng.normal(size=(B, D))
+        xh = x0[:, None, :] + 0.7 * rng.normal(size=(B, m, D))
+        loss, conf, inter, grad = oracle.energy_loss(xh, x0, beta, 1.3, 0.6)
+        num = np.zeros_like(xh)
+        h = 1e-6
+        for idx in np.ndindex(*xh.shape):
+            xp, xm = xh.copy(), xh.copy()
+            xp[idx] += h
+            xm[idx] -= h
+            num[idx] = (oracle.energy_loss(xp, x0, beta, 1.3, 0.6, want_grad=False)[0] -
+                        oracle.energy_loss(xm, x0, beta, 1.3, 0.6, want_grad=False)[0]) / (2 * h)
+        assert np.max(np.abs(num - grad)) <= 1e-7 * max(np.max(np.abs(grad)), 1e-12) + 1e-9, (B, m, D, beta)
+        shift = rng.normal(size=(B, 1, D))
+        l2, c2, i2, g2 = oracle.energy_loss(xh + shift, x0 + shift[:, 0], beta, 1.3, 0.6)
+        assert abs(l2 - loss) <= 1e-12 * abs(loss) + 1e-14 and np.allclose(g2, grad, rtol=1e-9, atol=1e-14)
+        perm, dperm = rng.permutation(m), rng.permutation(D)
+        l3, _, _, g3 = oracle.energy_loss(xh[:, perm][:, :, dperm], x0[:, dperm], beta, 1.3, 0.6)
+        assert abs(l3 - loss) <= 1e-12 * abs(loss) + 1e-14 and np.allclose(g3, grad[:, perm][:, :, dperm], rtol=1e-9, atol=1e-14)
