@@ -17,6 +17,19 @@ Tuning& tuning() {
 static thread_local int g_last_error = 0;
 void set_last_error(int e) { g_last_error = e; }
 
+// Multiprocessor count of the CURRENT device (cached per device: a process may drive several).
+int device_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
 static bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Register-resident plan: m in [2,8]; a row slab of ceil(nvec/cluster) vectors must fit
@@ -78,6 +91,11 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     // (m <= 8, any alignment) > blocked packed-fp32 kernel (m = 16, 32, aligned rows) > chunked smem-tile
     // kernel (any m <= 64)
     const int variant = tuning().variant;
+    if (variant == 0 || variant == 5) {
+        WavePlan wp = plan_wave(p.B, p.m, p.D, (int)sizeof(T), al);
+        if (wp.ok) return launch_energy_wave<T>(p, wp, stream);
+        if (variant == 5) return DDDM_ERR_UNSUPPORTED;
+    }
     if (variant == 0 || variant == 3) {
         SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al);
         if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
@@ -253,6 +271,7 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.threads")) t.threads = value;
     else if (!strcmp(key, "energy.ctas")) t.ctas = value;
     else if (!strcmp(key, "energy.cols")) t.cols = value;
+    else if (!strcmp(key, "energy.ksmem")) t.ksmem = value;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -266,6 +285,7 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.threads")) return t.threads;
     if (!strcmp(key, "energy.ctas")) return t.ctas;
     if (!strcmp(key, "energy.cols")) return t.cols;
+    if (!strcmp(key, "energy.ksmem")) return t.ksmem;
     return DDDM_ERR_BAD_ARGUMENT;
 }
 int dddm_set_trace_buffer(void* device_buffer) {
@@ -275,12 +295,18 @@ int dddm_set_trace_buffer(void* device_buffer) {
 unsigned long long dddm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) {
-    (void)B;
     if (!buf || buflen < 1) return DDDM_ERR_NULL_POINTER;
     const int es = dtype == 1 ? 2 : 4;
     const bool al = ((long)D * es) % 16 == 0;
     int n;
     const int variant = tuning().variant;
+    if (variant == 0 || variant == 5) {
+        WavePlan wp = plan_wave(B, m, D, es, al);
+        if (wp.ok)
+            return snprintf(buf, buflen, "wave<%s,M=%d,NV=%d> ldg.128 f32x2 register-resident cluster=1 threads=%d coef=%s",
+                            dtype == 1 ? "bf16" : "f32", m, wp.nv, wp.threads, wp.ksmem ? "smem" : "regs");
+        if (variant == 5) return snprintf(buf, buflen, "unsupported");
+    }
     if (variant == 0 || variant == 3) {
         SmemPlan sp = plan_smem(m, D, es, al);
         if (sp.ok)

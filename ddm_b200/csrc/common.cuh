@@ -18,11 +18,13 @@ void count_launch();
 struct Tuning {
     int cluster = 0;  // CTAs per row (0 = auto)
     int nv = 0;       // 16-byte vectors per thread (0 = auto)
-    int variant = 0;  // 0 auto, 1 register-resident, 2 generic smem/TMA tile, 3 TMA-staged packed-fp32 (m <= 8)
+    int variant = 0;  // 0 auto, 1 register-resident, 2 generic smem/TMA tile, 3 TMA-staged packed-fp32 (m <= 8),
+                      // 4 blocked (m = 16, 32), 5 single-wave register-resident (m <= 8, one CTA per SM)
     int threads = 0;  // threads per CTA for variant 3 (0 = auto)
     int pdl = 1;      // programmatic dependent launch (the prologue overlaps the previous kernel's tail; every
                       // kernel waits on cudaGridDependencySynchronize() before touching global memory)
     int cols = 0;     // experiment: columns per thread step of the bf16 variant-3 kernel (0 = default)
+    int ksmem = 0;    // single-wave kernel: pass-2 coefficients streamed from shared memory (1) or held in registers (0)
     int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
     void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)
 };

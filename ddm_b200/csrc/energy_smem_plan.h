@@ -13,6 +13,16 @@ struct SmemPlan {
 SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16);
 template <typename T>
 int launch_energy_smem(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
+// single-wave register-resident variant (energy_wave.cuh)
+struct WavePlan {
+    bool ok;
+    int threads;  // compute threads (a control warp is added at launch)
+    int nv;       // 16-byte vectors per thread
+    int ksmem;    // pass-2 coefficients streamed from shared memory instead of held in 72 registers
+};
+WavePlan plan_wave(int B, int m, int D, int elem_size, bool aligned16);
+template <typename T>
+int launch_energy_wave(const EnergyParams& p, const WavePlan& plan, cudaStream_t stream);
 // blocked variant for m = 16, 32 (energy_blk.cuh)
 SmemPlan plan_blk(int m, int D, int elem_size, bool aligned16);
 template <typename T>

@@ -59,8 +59,13 @@ def test_status_messages_and_validation(cabi):
 
 def test_kernel_plans(cabi):
     try:
-        assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
-        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
+        # one wave of rows (B <= #SMs): the latency kernel; many waves: the TMA-staged throughput kernel
+        assert cabi.describe_energy(128, 8, 3072).startswith("wave<f32,M=8,NV=3> ldg.128 f32x2 register-resident")
+        assert "threads=256" in cabi.describe_energy(128, 8, 3072)
+        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("wave<bf16,M=8,NV=")
+        assert cabi.describe_energy(4096, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
+        assert cabi.describe_energy(4096, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
+        assert cabi.describe_energy(128, 8, 12288).startswith("smem<f32,M=8>")  # row too wide for the register file
         assert cabi.describe_energy(512, 8, 2).startswith("reg<f32,M=8,VEC=1")
         cabi.set_tuning("energy.variant", 1)
         assert cabi.describe_energy(128, 8, 3072).startswith("reg<f32,M=8,VEC=4")

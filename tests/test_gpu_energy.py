@@ -34,8 +34,9 @@ def dev(cuda_device):
 
     _cabi.lib()
     yield cuda_device
-    for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.pdl", "energy.threads"):
+    for k in ("energy.cluster", "energy.nv", "energy.variant", "energy.threads", "energy.ksmem"):
         _cabi.set_tuning(k, 0)
+    _cabi.set_tuning("energy.pdl", 1)
 
 
 def _fused(xhat, x0, w, beta, lam, want_grad=True):
@@ -172,6 +173,63 @@ def test_ragged_shapes(dev, m, D):
         _check_case(xh.numpy(), x0.numpy(), beta, dev)
     xh, x0 = _synthetic(2, m, D, "late", seed=99)
     _check_case(xh.numpy(), x0.numpy(), 0.1, dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
+def test_wave_kernel_plans(dev):
+    """The single-wave register-resident kernel (variant 5, the path one launch of B <= #SMs rows takes): every
+    (threads, vectors per thread, coefficient placement) plan, fp32 and bf16, m = 2..8, rows that do not fill the
+    last vector slot, more rows than SMs (forced), fused and split-forward modes — against the fp64 oracle."""
+    from ddm_b200 import _cabi, ops
+
+    assert "wave<" in _cabi.describe_energy(128, 8, 3072), _cabi.describe_energy(128, 8, 3072)
+    assert "wave<" in _cabi.describe_energy(128, 8, 3072, "bf16")
+    assert "wave<" not in _cabi.describe_energy(4096, 8, 3072)  # many waves: the throughput kernel
+    seen = set()
+    try:
+        _cabi.set_tuning("energy.variant", 5)
+        for dtype, rel, name in ((torch.float32, FP32_REL, "f32"), (torch.bfloat16, BF16_REL, "bf16")):
+            vecw = 4 if name == "f32" else 8
+            for threads, nv in ((128, 1), (128, 2), (128, 3), (256, 1), (256, 2), (256, 3), (384, 1), (384, 2)):
+                for ksmem in (0, 1):
+                    _cabi.set_tuning("energy.threads", threads)
+                    _cabi.set_tuning("energy.nv", nv)
+                    _cabi.set_tuning("energy.ksmem", ksmem)
+                    # full tile, and a row that ends inside the last vector slot of some threads
+                    for D in (threads * nv * vecw, threads * nv * vecw - 5 * vecw):
+                        m = 8 if ksmem == 0 else 2 + (threads // 128 + nv) % 7
+                        B = 5
+                        xh, x0 = _synthetic(B, m, D, "late" if nv % 2 else "early", seed=threads + nv)
+                        beta = (0.1, 1.0, 2.0)[(nv + ksmem) % 3]
+                        xh, x0 = xh.to(dev).to(dtype), x0.to(dev).to(dtype)
+                        loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(),
+                                                                     beta, 1.3, 0.7)
+                        out, g = _fused(xh, x0, 0.7, beta, 1.3)
+                        seen.add(_cabi.describe_energy(B, m, D, name))
+                        scale = max(abs(conf), abs(inter))
+                        assert abs(out[1] - conf) <= FP32_REL * scale and abs(out[2] - inter) <= FP32_REL * scale
+                        assert abs(out[0] - loss) <= 2 * FP32_REL * 0.7 * scale
+                        assert _rel(g, grad) <= rel, (name, threads, nv, ksmem, D, _rel(g, grad))
+                        o2, dist = ops.energy_terms_fwd(xh, x0, beta)  # split forward on the same kernel
+                        o2 = o2.cpu().numpy().astype(np.float64)
+                        assert abs(o2[0] - conf) <= FP32_REL * scale and abs(o2[1] - inter) <= FP32_REL * scale
+        # more rows than SMs (several waves of one CTA per SM) and repeated launches on one workspace
+        for k in ("energy.threads", "energy.nv", "energy.ksmem"):
+            _cabi.set_tuning(k, 0)
+        xh, x0 = _synthetic(333, 8, 1024, "late", seed=3)
+        xh, x0 = xh.to(dev), x0.to(dev)
+        loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(), 0.1, 1.0, 0.5)
+        for _ in range(3):
+            out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
+            assert "wave<" in _cabi.describe_energy(333, 8, 1024)
+            assert abs(out[0] - loss) <= 2e-5 * abs(conf)
+            assert _rel(g, grad) <= FP32_REL
+        # forward only (no gradient buffer)
+        out, _ = _fused(xh, x0, 0.5, 0.1, 1.0, want_grad=False)
+        assert abs(out[0] - loss) <= 2e-5 * abs(conf)
+    finally:
+        for k in ("energy.variant", "energy.threads", "energy.nv", "energy.ksmem"):
+            _cabi.set_tuning(k, 0)
+    assert len(seen) >= 40, len(seen)
 
 
 def test_kernel_variants_agree(dev):

@@ -102,8 +102,8 @@ def main():
         configs = [dict(variant=3, cluster=c, threads=t, pdl=1) for c, t in
                    itertools.product((1, 2, 4, 8), (32, 64, 96, 128, 192, 256))]
     for cfg in configs:
-        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols"):
-            _cabi.set_tuning(f"energy.{k}", int(cfg.get(k, 0)))
+        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols", "ksmem"):
+            _cabi.set_tuning(f"energy.{k}", int(cfg.get(k, 1 if k == "pdl" else 0)))
         desc = _cabi.describe_energy(a.B, a.m, a.D, a.dtype)
         try:
             us, gbs = time_config(L, a.B, a.m, a.D, a.dtype, two_streams=a.two_streams, nstreams=a.streams, nsets_override=a.sets,
