@@ -85,6 +85,9 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     p.ticket = &ws->ticket;
     p.row_partials = reinterpret_cast<float*>(ws + 1);
     p.trace = static_cast<unsigned long long*>(tuning().trace);
+    p.window = tuning().window > 0 ? tuning().window : 3;
+    p.ld_hint = tuning().ldhint;
+    p.st_hint = tuning().sthint;
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
     // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel
@@ -272,6 +275,11 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.ctas")) t.ctas = value;
     else if (!strcmp(key, "energy.cols")) t.cols = value;
     else if (!strcmp(key, "energy.ksmem")) t.ksmem = value;
+    else if (!strcmp(key, "energy.loader")) t.loader = value;
+    else if (!strcmp(key, "energy.window")) t.window = value;
+    else if (!strcmp(key, "energy.ldhint")) t.ldhint = value;
+    else if (!strcmp(key, "energy.sthint")) t.sthint = value;
+    else if (!strcmp(key, "energy.nostore")) t.nostore = value;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -286,6 +294,11 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.ctas")) return t.ctas;
     if (!strcmp(key, "energy.cols")) return t.cols;
     if (!strcmp(key, "energy.ksmem")) return t.ksmem;
+    if (!strcmp(key, "energy.loader")) return t.loader;
+    if (!strcmp(key, "energy.window")) return t.window;
+    if (!strcmp(key, "energy.ldhint")) return t.ldhint;
+    if (!strcmp(key, "energy.sthint")) return t.sthint;
+    if (!strcmp(key, "energy.nostore")) return t.nostore;
     return DDDM_ERR_BAD_ARGUMENT;
 }
 int dddm_set_trace_buffer(void* device_buffer) {
@@ -304,15 +317,17 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
         WavePlan wp = plan_wave(B, m, D, es, al);
         if (wp.ok)
             return snprintf(buf, buflen, "wave<%s,M=%d,NV=%d> ldg.128 f32x2 register-resident cluster=1 threads=%d coef=%s",
-                            dtype == 1 ? "bf16" : "f32", m, wp.nv, wp.threads, wp.ksmem ? "smem" : "regs");
+                            dtype == 1 ? "bf16" : "f32", m, wp.nv, wp.threads, wp.ksmem == 2 ? "pair-major" : (wp.ksmem ? "smem" : "regs"));
         if (variant == 5) return snprintf(buf, buflen, "unsupported");
     }
     if (variant == 0 || variant == 3) {
         SmemPlan sp = plan_smem(m, D, es, al);
-        if (sp.ok)
-            return snprintf(buf, buflen, "smem<%s,M=%d> tma-bulk f32x2 cluster=%d threads=%d slab_vecs=%d chunk_vecs=%d smem=%zu",
-                            dtype == 1 ? "bf16" : "f32", m, sp.cluster, sp.threads, sp.slab_vecs, sp.chunk_vecs,
-                            sp.smem_bytes);
+        if (sp.ok) {
+            const bool ldgsts = tuning().loader == 2;
+            return snprintf(buf, buflen, "smem<%s,M=%d> %s f32x2 cluster=%d threads=%d slab_vecs=%d chunk_vecs=%d smem=%zu",
+                            dtype == 1 ? "bf16" : "f32", m, ldgsts ? "cp.async" : "tma-bulk", sp.cluster, sp.threads,
+                            sp.slab_vecs, sp.chunk_vecs, sp.smem_bytes);
+        }
         if (variant == 3) return snprintf(buf, buflen, "unsupported");
     }
     if (variant == 0 || variant == 1) {

@@ -25,6 +25,11 @@ struct Tuning {
                       // kernel waits on cudaGridDependencySynchronize() before touching global memory)
     int cols = 0;     // experiment: columns per thread step of the bf16 variant-3 kernel (0 = default)
     int ksmem = 0;    // single-wave kernel: pass-2 coefficients streamed from shared memory (1) or held in registers (0)
+    int loader = 0;   // TMA-staged kernel: 0 auto, 1 TMA bulk copies, 2 cp.async commit groups (thread-private slots)
+    int window = 0;   // cp.async loader: column chunks in flight per CTA (0 = default)
+    int ldhint = 0;   // single-wave kernel: L2 eviction priority of the input loads (0 normal, 1 first, 2 last, 3 unchanged)
+    int sthint = 0;   // ... and of the gradient stores
+    int nostore = 0;  // diagnostics: pass 2 without its global stores (fp32/bf16 m = 8, 256 x 3 plan only)
     int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
     void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)
 };

@@ -82,7 +82,37 @@ __host__ __device__ constexpr int pair_slot(int i, int j) {  // i < j
         if (p.trace != nullptr) p.trace[((long)b * cluster_size + rank) * 16 + (slot)] = globaltimer_ns(); \
     } while (0)
 
-template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false>
+// cp.async (LDGSTS) of one thread step; completion is tracked per thread in commit groups.
+template <int BYTES>
+__device__ __forceinline__ void cp_async_step(void* dst, const void* src) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `pending` of this thread's most recent commit groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+
+// LOADER 0: the tile is staged by 1-D TMA bulk copies, one per tile row and column chunk, completion per chunk on an
+//           mbarrier.  Costs no issue slots: the throughput path (two CTAs of different launches per SM).
+// LOADER 1: every compute thread copies exactly the steps it will read itself with cp.async, one commit group per
+//           column chunk.  On a single launch the bulk copies of a CTA all complete together at the END of the load
+//           phase (measured: first chunk after 2.6 us of 3.7), so pass 1 could not start before the whole tile had
+//           landed; commit groups complete in issue order, so pass 1 follows the loads chunk by chunk and hides inside
+//           the HBM-bound load phase.  The slots are thread-private: no barrier between the copy and its use.
+template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false, int LOADER = 0>
 __global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
 energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
@@ -122,7 +152,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         for (int w = nwarps; w < kSmemMaxThreads / 32; ++w)
             for (int s = lane; s < P; s += 32) s_warp[w][s] = 0.f;
     }
-    if (control && lane == 0) {
+    if (LOADER == 0 && control && lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             mbar_init(&s_bar[c], 1);
             mbar_expect_tx(&s_bar[c], (uint32_t)min(chunk_vecs, nv - c * chunk_vecs) * 16u * (uint32_t)(M + 1));
@@ -134,7 +164,33 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     if (tid == 0) DDDM_TRACE(1);
     // One bulk copy costs its issuing thread ~45 ns (tools/trace_energy.py), so the (M+1) x nchunks copies are dealt
     // to ALL warps (row r -> warp r mod nwarps+1, chunk-major): the tile is requested 5x sooner than from one warp.
-    if (lane == 0) {
+    // cp.async loader: at most `window` column chunks of the CTA are in flight.  All 128 rows of a launch start
+    // together; with every request of every SM queued at once the memory system serves them in no particular order
+    // and the FIRST chunk lands after 60-100 % of the load phase (measured) — with a bounded window the queues stay
+    // short, chunks land in order and pass 1 follows them.
+    constexpr int SB = Step<T, COLS>::kBytes;
+    const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.xhat) + (long)b * M * p.D + v_begin * VEC);
+    const unsigned char* csrc = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC);
+    const size_t grow_bytes = (size_t)p.D * sizeof(T);
+    const int window = min(max(p.window, 1), 8);
+    auto issue_chunk = [&](int c) {  // every thread commits one group per call (an empty one past the last chunk)
+        if (c < nchunks) {
+            const int q_end = min(nq, (c + 1) * chunk_q);
+            for (int q = c * chunk_q + tid; q < q_end; q += nthr) {
+#pragma unroll
+                for (int r = 0; r < M; ++r)
+                    cp_async_step<SB>(s_tile + (size_t)r * row_bytes + (size_t)q * SB, xsrc + (size_t)r * grow_bytes + (size_t)q * SB);
+                cp_async_step<SB>(s_tile + (size_t)M * row_bytes + (size_t)q * SB, csrc + (size_t)q * SB);
+            }
+        }
+        cp_async_commit();
+    };
+    if constexpr (LOADER == 1) {
+        if (!control) {
+            for (int c = 0; c < window; ++c) issue_chunk(c);
+        }
+        if (control && lane == 0) DDDM_TRACE(6);
+    } else if (lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             const int c0 = c * chunk_vecs;
             const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
@@ -162,7 +218,12 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     for (int s = 0; s < P; ++s) acc2[s] = make_float2(0.f, 0.f);
     for (int q = (control || bwd) ? nq : tid; q < nq; q += nthr) {
         if ((q - tid) % chunk_q == 0) {  // warp-uniform: entering a new chunk
-            mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+            if constexpr (LOADER == 1) {
+                cp_async_wait_pending(window - 1);  // chunk c has landed (window groups were committed after c - 1)
+                issue_chunk((q - tid) / chunk_q + window);
+            } else {
+                mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+            }
             if (tid == 0 && q == 0) DDDM_TRACE(2);
         }
         float2 x[M + 1][NP];
@@ -255,7 +316,9 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         // grad_x0 exists only in the backward instantiation (the fused loss never differentiates w.r.t. the data)
         T* __restrict__ g0row = (BWD && p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
         for (int q = tid; q < nq; q += nthr) {
-            if (bwd && (q - tid) % chunk_q == 0) mbar_wait(&s_bar[(q - tid) / chunk_q], 0);  // no pass 1 waited for it
+            if (bwd && (q - tid) % chunk_q == 0) {  // no pass 1 waited for it
+                mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+            }
             float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
             for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);

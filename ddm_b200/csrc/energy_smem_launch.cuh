@@ -5,6 +5,8 @@
 
 namespace dddm {
 
+int device_sm_count();  // api.cu
+
 template <typename T, int M>
 int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
     // 4 columns per thread step (fewest LDS / conversion / loop instructions per column).  fp32: the 110 KB tile
@@ -14,12 +16,19 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
     constexpr int kMinCtas = (sizeof(T) == 4) ? 2 : 3;
     auto kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas>;
     int which = 0;
+    // loader: TMA bulk copies; tuning "energy.loader" = 2 selects cp.async commit groups with a bounded window of
+    // chunks in flight (measured equal on a single launch, 8.89 against 8.94 us: the load phase is HBM-bound either way)
+    const bool ldgsts = tuning().loader == 2;
+    if (ldgsts && p.mode != kModeBwd) {
+        kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas, false, 1>;
+        which = 4;
+    }
     if (p.mode == kModeBwd) {
         kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas, true>;
         which = 3;
     }
     if constexpr (sizeof(T) == 2) {
-        if (p.mode == kModeBwd) {
+        if (p.mode == kModeBwd || which == 4) {
         } else if (tuning().ctas == 4) {  // experiment: the 4-CTA register cap (96 registers, ~170 B of spills)
             kernel = energy_fused_smem_kernel<T, M, 4, 4>;
             which = 1;
@@ -28,7 +37,7 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
             which = 2;
         }
     }
-    static size_t configured[4] = {0, 0, 0, 0};
+    static size_t configured[5] = {0, 0, 0, 0, 0};
     size_t& conf = configured[which];
     if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);

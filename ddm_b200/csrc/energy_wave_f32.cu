@@ -11,8 +11,13 @@ WavePlan plan_wave(int B, int m, int D, int elem_size, bool aligned16) {
     const int vecw = 16 / elem_size;
     if (m < 2 || m > 8 || D < 1 || !aligned16 || D % vecw != 0) return w;
     const Tuning& t = tuning();
-    // one wave, one CTA per SM: beyond that the throughput kernels (two CTAs per SM, rows overlapping) win
-    if (t.variant != 5 && B > device_sm_count()) return w;
+    // Opt-in (tuning "energy.variant" = 5).  Measured on B200 at B=128, m=8, D=3072 (profiles/r02_k1_single_launch.md):
+    // a single launch is bound by the HBM-saturated load phase (the previous launch's dirty gradient lines are
+    // written back while the next inputs are read) and by the serial pass 2, not by how the row is staged: fp32
+    // 9.1-9.3 us here against 8.9 us for the TMA-staged kernel, bf16 7.7 against 8.1 us; with several launches in
+    // flight the TMA-staged kernel (two CTAs per SM) is far ahead (4.1 against 5.4 us).
+    if (t.variant != 5) return w;
+    (void)B;
     const long nvec = D / vecw;
     int threads = t.threads, nv = t.nv;
     if (!(threads == 128 || threads == 256 || threads == 384) || nv < 1 || nv > 3) {
@@ -23,7 +28,7 @@ WavePlan plan_wave(int B, int m, int D, int elem_size, bool aligned16) {
     if ((long)threads * nv < nvec || nv > 3 || (threads == 384 && nv > 2)) return w;
     w.threads = threads;
     w.nv = nv;
-    w.ksmem = t.ksmem > 0 ? 1 : 0;
+    w.ksmem = 2;  // pair-major pass 2
     w.ok = true;
     return w;
 }

@@ -9,7 +9,7 @@ namespace dddm {
 // under the one-CTA-per-SM cap (224 registers at 288 threads, 152 at 416).
 template <typename T, int M>
 int launch_energy_wave_m(const EnergyParams& p, const WavePlan& plan, cudaStream_t stream) {
-    const bool ks = plan.ksmem != 0;
+    const int ks = plan.ksmem;
     switch (plan.threads * 10 + plan.nv) {
         case 1281: return launch_energy_wave_cfg<T, M, 1, 128>(p, ks, stream);
         case 1282: return launch_energy_wave_cfg<T, M, 2, 128>(p, ks, stream);

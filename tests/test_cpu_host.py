@@ -59,13 +59,16 @@ def test_status_messages_and_validation(cabi):
 
 def test_kernel_plans(cabi):
     try:
-        # one wave of rows (B <= #SMs): the latency kernel; many waves: the TMA-staged throughput kernel
+        assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
+        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
+        cabi.set_tuning("energy.loader", 2)
+        assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> cp.async f32x2")
+        cabi.set_tuning("energy.loader", 0)
+        cabi.set_tuning("energy.variant", 5)  # the single-wave register-resident kernel is opt-in
         assert cabi.describe_energy(128, 8, 3072).startswith("wave<f32,M=8,NV=3> ldg.128 f32x2 register-resident")
         assert "threads=256" in cabi.describe_energy(128, 8, 3072)
-        assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("wave<bf16,M=8,NV=")
-        assert cabi.describe_energy(4096, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
-        assert cabi.describe_energy(4096, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
-        assert cabi.describe_energy(128, 8, 12288).startswith("smem<f32,M=8>")  # row too wide for the register file
+        assert cabi.describe_energy(128, 8, 12288) == "unsupported"  # row too wide for the register file
+        cabi.set_tuning("energy.variant", 0)
         assert cabi.describe_energy(512, 8, 2).startswith("reg<f32,M=8,VEC=1")
         cabi.set_tuning("energy.variant", 1)
         assert cabi.describe_energy(128, 8, 3072).startswith("reg<f32,M=8,VEC=4")
@@ -85,6 +88,7 @@ def test_kernel_plans(cabi):
     finally:
         cabi.set_tuning("energy.variant", 0)
         cabi.set_tuning("energy.cluster", 0)
+        cabi.set_tuning("energy.loader", 0)
 
 
 def test_cuda_only_guards():
@@ -197,7 +201,14 @@ def test_sass_shows_tma_bulk_copies_and_packed_fp32():
     smem = [k for k in per_kernel if "energy_fused_smem_kernelIfLi8" in k.split("\n", 1)[0]]
     blk = [k for k in per_kernel if "energy_fused_blk_kernelIfLi32" in k.split("\n", 1)[0]]
     assert smem and blk
+    ldgsts = [k for k in smem if "ELb0ELi1EEEv" in k.split("\n", 1)[0]]  # the cp.async loader instantiation
+    assert ldgsts and len(ldgsts) < len(smem)
+    for k in ldgsts:
+        assert "LDGSTS" in k and "LDGDEPBAR" in k, "cp.async loader: LDGSTS + commit groups expected"
     for k in smem + blk:
+        if k in ldgsts:
+            continue
         assert "UBLKCP" in k and "SYNCS" in k, "TMA bulk copy + mbarrier expected"
+    for k in smem + blk:
         assert k.count("FFMA2") > 80 and k.count("FADD2") > 80, "packed fp32 arithmetic expected"  # bwd-only build: 112 / 86
     assert "HMMA" not in sass and "HGMMA" not in sass

@@ -73,7 +73,12 @@ def main():
         e1.synchronize()
     print(f"kernel: {desc}; streams={a.streams}; tune={a.tune or 'auto'}; "
           f"{e0.elapsed_time(e1) * 1e3 / a.launches:.2f} us/launch (events, with tracing on)")
-    tr = np.stack([s[6].cpu().numpy().reshape(a.B * cluster, 16)[:, :12] for s in sets]).astype(np.int64)  # [launch, cta, 8]
+    full = np.stack([s[6].cpu().numpy().reshape(a.B * cluster, 16) for s in sets]).astype(np.int64)
+    tr = full[:, :, :12]  # [launch, cta, stage]
+    if full.shape[0] > 2 and (full[2:, :, 13] > 0).all():  # SM cycle counter stamped next to inputs_ready / pass2_done: effective SM clock
+        mhz = (full[2:, :, 13] - full[2:, :, 12]) / np.maximum(1, tr[2:, :, 5] - tr[2:, :, 1]) * 1e3
+        print(f"SM clock between inputs_ready and pass2_done: median {np.median(mhz):.0f} MHz (p5 {np.percentile(mhz, 5):.0f}, "
+              f"p95 {np.percentile(mhz, 95):.0f})")
     t0 = tr[:, :, 0].min(axis=1)  # first CTA entry of each launch
     rel = tr - t0[:, None, None]
     res = np.diff(np.unique(tr[:, :, 0].ravel()))
