@@ -35,6 +35,9 @@ SIGNATURES = {
                                       c_int, c_int, c_float, c_float, c_void_p]),
     "dddm_energy_fused_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_float, c_float, c_void_p]),
+    "dddm_energy_fused_bf16_x0f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int,
+                                             c_int, c_int, c_float, c_float, c_void_p]),
+    "dddm_energy_fused_bf16_x0f32_supported": (c_int, [c_int, c_int]),
     "dddm_energy_terms_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_float, c_void_p]),
     "dddm_energy_terms_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -76,6 +79,7 @@ SIGNATURES = {
     "dddm_session_enqueue_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float,
                                           c_void_p, c_void_p]),
     "dddm_session_wait": (c_int, [c_void_p]),
+    "dddm_session_packed_layout": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dddm_host_alloc": (c_void_p, [c_size_t]),
     "dddm_host_free": (None, [c_void_p]),
     "dddm_last_error": (c_int, []),

@@ -94,6 +94,11 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     // (m <= 8, any alignment) > blocked packed-fp32 kernel (m = 16, 32, aligned rows) > chunked smem-tile
     // kernel (any m <= 64)
     const int variant = tuning().variant;
+    if (p.x0_f32) {  // bf16 draws + fp32 x0: the TMA-staged kernel is the only one with a mixed tile
+        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 2);
+        if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
+        return DDDM_ERR_UNSUPPORTED;
+    }
     if (variant == 0 || variant == 5) {
         WavePlan wp = plan_wave(p.B, p.m, p.D, (int)sizeof(T), al);
         if (wp.ok) return launch_energy_wave<T>(p, wp, stream);
@@ -120,8 +125,9 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
 }
 
 template <typename T>
-static int energy_fused(const T* xhat, const T* x0, const float* weight_dev, float weight_scale, T* grad, float* out,
-                        void* workspace, int B, int m, int D, float beta, float lam, cudaStream_t stream) {
+static int energy_fused(const T* xhat, const void* x0, const float* weight_dev, float weight_scale, T* grad, float* out,
+                        void* workspace, int B, int m, int D, float beta, float lam, cudaStream_t stream,
+                        bool x0_f32 = false) {
     int st = validate(xhat, x0, out, workspace, B, m, D);
     if (st != DDDM_OK) return st;
     if (!weight_dev) return DDDM_ERR_NULL_POINTER;
@@ -138,6 +144,7 @@ static int energy_fused(const T* xhat, const T* x0, const float* weight_dev, flo
     p.lam = lam;
     p.pw = make_pow_spec(beta);
     p.mode = kModeLoss;
+    p.x0_f32 = x0_f32 ? 1 : 0;
     return run_forward<T>(p, workspace, stream);
 }
 
@@ -241,6 +248,15 @@ int dddm_energy_fused_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const flo
                            float lam, dddm_stream_t stream) {
     return energy_fused<bf16>((const bf16*)xhat, (const bf16*)x0, weight_dev, weight_scale, (bf16*)grad_xhat, out,
                               workspace, B, m, D, beta, lam, (cudaStream_t)stream);
+}
+int dddm_energy_fused_bf16_x0f32(const dddm_bf16* xhat, const float* x0, const float* weight_dev, float weight_scale,
+                                 dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
+                                 float lam, dddm_stream_t stream) {
+    return energy_fused<bf16>((const bf16*)xhat, x0, weight_dev, weight_scale, (bf16*)grad_xhat, out, workspace, B, m, D,
+                              beta, lam, (cudaStream_t)stream, true);
+}
+int dddm_energy_fused_bf16_x0f32_supported(int m, int D) {
+    return plan_smem(m, D, 2, ((long)D * 2) % 16 == 0, 2).ok ? 1 : 0;
 }
 int dddm_energy_terms_fwd_f32(const float* xhat, const float* x0, float* dist, float* out, void* workspace, int B,
                               int m, int D, float beta, dddm_stream_t stream) {

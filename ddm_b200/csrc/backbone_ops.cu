@@ -276,16 +276,7 @@ colsum_partial_kernel(const T* __restrict__ a, float* __restrict__ part, long N,
     }
 }
 
-static int g_sms = 0;
-static int sms() {
-    if (g_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
-}
+static int sms() { return device_sm_count(); }  // per-device cache in api.cu
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T, int NV>
@@ -318,10 +309,8 @@ static int ln_bwd_nv(const T* dy, const T* x, const float* mean, const float* rs
                      T* dbeta, float* part, int grid, long N, int C, cudaStream_t stream) {
     auto kernel = layer_norm_bwd_kernel<T, NV>;
     const size_t smem = (size_t)kLnWarps * 2 * C * sizeof(float);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    static SmemOptIn configured;  // per instantiation and per device
+    if (int e = configured.ensure(kernel, smem, 48 * 1024)) return e;
     kernel<<<grid, kLnWarps * 32, smem, stream>>>(dy, x, mean, rstd, gamma, dx, part, N, C);
     count_launch();
     fold_partials_kernel<T><<<(2 * C + 31) / 32, 256, 0, stream>>>(part, grid, 2 * C, dgamma, dbeta, C);

@@ -35,6 +35,25 @@ struct Tuning {
 };
 Tuning& tuning();
 
+// ---- per-device host-side caches (a process may drive several GPUs; function attributes are per device) -------
+int device_sm_count();  // multiprocessors of the CURRENT device (api.cu)
+constexpr int kMaxDevices = 64;
+// Largest dynamic shared-memory size a kernel has been opted into, per device.
+struct SmemOptIn {
+    size_t per_device[kMaxDevices] = {};
+    template <typename K>
+    int ensure(K kernel, size_t bytes, size_t threshold) {
+        if (bytes <= threshold) return 0;
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = -1;
+        if (dev >= 0 && bytes <= per_device[dev]) return 0;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 0) per_device[dev] = bytes;  // benign race: a concurrent caller at worst repeats the opt-in
+        return 0;
+    }
+};
+
 // ---- element traits ----------------------------------------------------------------------
 template <typename T>
 struct Elem;

@@ -9,16 +9,7 @@
 
 namespace dddm {
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }  // per-device cache in api.cu
 
 template <typename T>
 static bool aligned16(const T* p) {

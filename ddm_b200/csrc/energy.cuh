@@ -29,6 +29,7 @@ struct EnergyParams {
     float lam;
     PowSpec pw;
     int mode;
+    int x0_f32;                 // bf16 kernels: x0 is fp32 (mixed entry point; TMA-staged kernel only)
     int window;                 // cp.async loader of the TMA-staged kernel: column chunks in flight per CTA
     int ld_hint, st_hint;       // L2 eviction priority of the streaming loads / stores (single-wave kernel; 0 = normal)
     unsigned long long* trace;  // diagnostics: 8 globaltimer stamps per CTA, or null (dddm_set_trace_buffer)

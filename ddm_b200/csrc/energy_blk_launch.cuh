@@ -10,13 +10,8 @@ int launch_energy_blk_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_
     // two builds: register cap for 2 CTAs per SM (168) or uncapped for tiles that leave room for only one
     const bool two = plan.smem_bytes <= 104 * 1024 && tuning().ctas != 1;
     auto kernel = two ? energy_fused_blk_kernel<T, M, 2> : energy_fused_blk_kernel<T, M, 1>;
-    static size_t configured[2] = {0, 0};
-    size_t& conf = configured[two ? 1 : 0];
-    if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        conf = plan.smem_bytes;
-    }
+    static SmemOptIn configured[2];  // per instantiation and per device
+    if (int e = configured[two ? 1 : 0].ensure(kernel, plan.smem_bytes, 40 * 1024)) return e;
     return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
                              p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);
 }

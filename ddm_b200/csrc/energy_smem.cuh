@@ -16,6 +16,8 @@
 
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "energy.cuh"
 #include "energy_smem_plan.h"
 #include "energy_tile.cuh"  // mbarrier / TMA bulk helpers
@@ -112,12 +114,17 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {
 //           phase (measured: first chunk after 2.6 us of 3.7), so pass 1 could not start before the whole tile had
 //           landed; commit groups complete in issue order, so pass 1 follows the loads chunk by chunk and hides inside
 //           the HBM-bound load phase.  The slots are thread-private: no barrier between the copy and its use.
-template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false, int LOADER = 0>
+// X0F32 (bf16 draws only): x0 stays fp32 in memory and in the tile — the mixed entry point a bf16 backbone uses
+//           (bf16 xhat in, fp32 data, bf16 gradient out), so that neither xhat is up-converted nor x0 rounded.
+template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false, int LOADER = 0, bool X0F32 = false>
 __global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
 energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
     constexpr int P = M * (M + 1) / 2;
     constexpr int VEC = Elem<T>::kVec;
+    static_assert(!X0F32 || (sizeof(T) == 2 && !BWD), "mixed entry: bf16 draws, fused loss only");
+    constexpr int X0S = X0F32 ? 2 : 1;  // bytes of the x0 tile row relative to a draw row
+    using T0 = typename std::conditional<X0F32, float, T>::type;
     constexpr int U = Step<T, COLS>::kPerVec;
     constexpr int NP = Step<T, COLS>::kPairs;
     using WR = WarpReduce<P>;
@@ -155,7 +162,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     if (LOADER == 0 && control && lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             mbar_init(&s_bar[c], 1);
-            mbar_expect_tx(&s_bar[c], (uint32_t)min(chunk_vecs, nv - c * chunk_vecs) * 16u * (uint32_t)(M + 1));
+            mbar_expect_tx(&s_bar[c], (uint32_t)min(chunk_vecs, nv - c * chunk_vecs) * 16u * (uint32_t)(M + X0S));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the barriers visible to the TMA (async proxy)
     }
@@ -170,7 +177,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     // short, chunks land in order and pass 1 follows them.
     constexpr int SB = Step<T, COLS>::kBytes;
     const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.xhat) + (long)b * M * p.D + v_begin * VEC);
-    const unsigned char* csrc = reinterpret_cast<const unsigned char*>(static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC);
+    const unsigned char* csrc = reinterpret_cast<const unsigned char*>(static_cast<const T0*>(p.x0) + (long)b * p.D + v_begin * VEC);
     const size_t grow_bytes = (size_t)p.D * sizeof(T);
     const int window = min(max(p.window, 1), 8);
     auto issue_chunk = [&](int c) {  // every thread commits one group per call (an empty one past the last chunk)
@@ -180,7 +187,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
 #pragma unroll
                 for (int r = 0; r < M; ++r)
                     cp_async_step<SB>(s_tile + (size_t)r * row_bytes + (size_t)q * SB, xsrc + (size_t)r * grow_bytes + (size_t)q * SB);
-                cp_async_step<SB>(s_tile + (size_t)M * row_bytes + (size_t)q * SB, csrc + (size_t)q * SB);
+                cp_async_step<SB * X0S>(s_tile + (size_t)M * row_bytes + (size_t)q * SB * X0S, csrc + (size_t)q * SB * X0S);
             }
         }
         cp_async_commit();
@@ -195,9 +202,14 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             const int c0 = c * chunk_vecs;
             const uint32_t bytes = (uint32_t)min(chunk_vecs, nv - c0) * 16u;
             for (int r = warp; r <= M; r += nwarps + 1) {
-                const T* src = (r < M) ? static_cast<const T*>(p.xhat) + ((long)b * M + r) * p.D + v_begin * VEC
-                                       : static_cast<const T*>(p.x0) + (long)b * p.D + v_begin * VEC;
-                tma_bulk_g2s(s_tile + (size_t)r * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
+                if (r < M) {
+                    const T* src = static_cast<const T*>(p.xhat) + ((long)b * M + r) * p.D + v_begin * VEC;
+                    tma_bulk_g2s(s_tile + (size_t)r * row_bytes + (size_t)c0 * 16, src + (long)c0 * VEC, bytes, &s_bar[c]);
+                } else {
+                    const T0* src = static_cast<const T0*>(p.x0) + (long)b * p.D + v_begin * VEC;
+                    tma_bulk_g2s(s_tile + (size_t)M * row_bytes + (size_t)c0 * 16 * X0S, src + (long)c0 * VEC, bytes * X0S,
+                                 &s_bar[c]);
+                }
             }
         }
         if (control) DDDM_TRACE(6);
@@ -228,7 +240,8 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         }
         float2 x[M + 1][NP];
 #pragma unroll
-        for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+        for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+        lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
 #pragma unroll
         for (int h = 0; h < NP; ++h) {
 #pragma unroll
@@ -321,7 +334,8 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             }
             float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
-            for (int r = 0; r <= M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+            for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+            lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
 #pragma unroll
             for (int h = 0; h < NP; ++h) {
 #pragma unroll

@@ -3,7 +3,7 @@
 
 namespace dddm {
 
-SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16) {
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows) {
     SmemPlan s{};
     s.ok = false;
     const int vecw = 16 / elem_size;
@@ -15,10 +15,10 @@ SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16) {
         // auto: whole rows per CTA whenever the (m+1) x D tile leaves room for two CTAs per SM
         // (measured on B200: fewer, fatter CTAs beat D-split clusters — no DSMEM round trip)
         cluster = 1;
-        while (cluster < 8 && (size_t)(m + 1) * ((nvec + cluster - 1) / cluster) * 16 > 112 * 1024) cluster *= 2;
+        while (cluster < 8 && (size_t)(m + x0_rows) * ((nvec + cluster - 1) / cluster) * 16 > 112 * 1024) cluster *= 2;
     }
     const long slab = (nvec + cluster - 1) / cluster;
-    const size_t smem = (size_t)(m + 1) * slab * 16;
+    const size_t smem = (size_t)(m + x0_rows) * slab * 16;  // x0_rows = 2: fp32 x0 next to bf16 draws (mixed entry)
     if (smem > 200 * 1024) return s;  // slab too wide: the chunked tile kernel handles it
     int threads = t.threads;
     if (threads < 32 || threads > kSmemMaxThreads || threads % 32) {

@@ -5,8 +5,6 @@
 
 namespace dddm {
 
-int device_sm_count();  // api.cu
-
 template <typename T, int M>
 int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream) {
     // 4 columns per thread step (fewest LDS / conversion / loop instructions per column).  fp32: the 110 KB tile
@@ -28,7 +26,11 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
         which = 3;
     }
     if constexpr (sizeof(T) == 2) {
-        if (p.mode == kModeBwd || which == 4) {
+        if (p.x0_f32) {  // mixed entry: fp32 x0 beside bf16 draws (fused loss only; TMA loader)
+            if (p.mode != kModeLoss) return DDDM_ERR_UNSUPPORTED;
+            kernel = energy_fused_smem_kernel<T, M, kCols, kMinCtas, false, 0, true>;
+            which = 5;
+        } else if (p.mode == kModeBwd || which == 4) {
         } else if (tuning().ctas == 4) {  // experiment: the 4-CTA register cap (96 registers, ~170 B of spills)
             kernel = energy_fused_smem_kernel<T, M, 4, 4>;
             which = 1;
@@ -37,13 +39,8 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
             which = 2;
         }
     }
-    static size_t configured[5] = {0, 0, 0, 0, 0};
-    size_t& conf = configured[which];
-    if (plan.smem_bytes > 40 * 1024 && plan.smem_bytes > conf) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        conf = plan.smem_bytes;
-    }
+    static SmemOptIn configured[6];  // per instantiation and per device
+    if (int e = configured[which].ensure(kernel, plan.smem_bytes, 40 * 1024)) return e;
     // the backward needs no cross-CTA sum: same grid, but the D-slabs of a row run as independent CTAs
     const int cluster = (p.mode == kModeBwd) ? 1 : plan.cluster;
     return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, cluster, stream,

@@ -10,7 +10,7 @@ struct SmemPlan {
     int cluster, threads, slab_vecs, chunk_vecs;
     size_t smem_bytes;
 };
-SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16);
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows = 1);
 template <typename T>
 int launch_energy_smem(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
 // single-wave register-resident variant (energy_wave.cuh)

@@ -8,12 +8,8 @@ namespace dddm {
 template <typename T, int VEC>
 int launch_tile_impl(const EnergyParams& p, const TilePlan& plan, bool from_dist, cudaStream_t stream) {
     auto kernel = energy_tile_kernel<T, VEC>;
-    static size_t configured = 0;  // per instantiation: largest dynamic smem opted into so far
-    if (plan.smem_bytes > 48 * 1024 && plan.smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        configured = plan.smem_bytes;
-    }
+    static SmemOptIn configured;  // per instantiation and per device
+    if (int e = configured.ensure(kernel, plan.smem_bytes, 48 * 1024)) return e;
     TileArgs a{};
     a.slab_cols = plan.slab_cols;
     a.chunk_cols = plan.chunk_cols;

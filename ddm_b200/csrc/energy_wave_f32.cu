@@ -3,8 +3,6 @@
 
 namespace dddm {
 
-int device_sm_count();  // api.cu (per-device cache)
-
 WavePlan plan_wave(int B, int m, int D, int elem_size, bool aligned16) {
     WavePlan w{};
     w.ok = false;

@@ -2,9 +2,12 @@
 //
 // What a reference-side binding without device tensors calls, and what bench.py reports as `e2e`:
 // host -> device copies of (xhat, x0, t), K4 (logistic weight sum) + K1 (fused energy score),
-// device -> host copies of {loss, conf, inter, W} and dloss/dxhat.  Three rotating buffer sets and
+// device -> host copies of {loss, conf, inter, W} and dloss/dxhat.  Four rotating buffer sets and
 // one stream per direction let step k+1's upload and step k-1's download overlap step k's kernels
 // (PCIe is full duplex); every dependency is an event, nothing blocks the host until _wait.
+// A slot's inputs live in ONE device allocation [xhat | x0 | t] and its outputs in one [grad | out]: when the
+// caller's host buffers have the same packed layout (dddm_session_packed_offsets) a step is exactly one
+// cudaMemcpyAsync per direction; separate host pointers still work and cost three + two copies.
 #include <cstdlib>
 #include <new>
 
@@ -15,10 +18,13 @@ void set_last_error(int e);
 }
 
 struct dddm_session {
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 4;
     int B, m, D, dtype, device;
     size_t esz;
+    size_t nx, n0, off_x0, off_t, in_bytes, off_out, out_bytes;  // packed layouts (offsets are 256-byte aligned)
     struct Slot {
+        unsigned char* in = nullptr;    // [xhat | x0 | t]
+        unsigned char* outb = nullptr;  // [grad | out[4]]
         void* xhat = nullptr;
         void* x0 = nullptr;
         void* grad = nullptr;
@@ -47,23 +53,27 @@ static int session_alloc(dddm_session* s) {
     SESSION_TRY(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
     SESSION_TRY(cudaStreamCreateWithFlags(&s->s_run, cudaStreamNonBlocking));
     SESSION_TRY(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
-    const size_t nx = (size_t)s->B * s->m * s->D * s->esz, n0 = (size_t)s->B * s->D * s->esz;
     const size_t nws = dddm_energy_workspace_bytes(s->B, s->m);
     for (auto& k : s->slot) {
-        SESSION_TRY(cudaMalloc(&k.xhat, nx));
-        SESSION_TRY(cudaMalloc(&k.x0, n0));
-        SESSION_TRY(cudaMalloc(&k.grad, nx));
-        SESSION_TRY(cudaMalloc((void**)&k.t, (size_t)s->B * sizeof(float)));
+        SESSION_TRY(cudaMalloc((void**)&k.in, s->in_bytes));
+        SESSION_TRY(cudaMalloc((void**)&k.outb, s->out_bytes));
+        k.xhat = k.in;
+        k.x0 = k.in + s->off_x0;
+        k.t = reinterpret_cast<float*>(k.in + s->off_t);
+        k.grad = k.outb;
+        k.out = reinterpret_cast<float*>(k.outb + s->off_out);
         SESSION_TRY(cudaMalloc((void**)&k.wsum, sizeof(float)));
-        SESSION_TRY(cudaMalloc((void**)&k.out, 4 * sizeof(float)));
         SESSION_TRY(cudaMalloc(&k.ws, nws));
-        SESSION_TRY(cudaMemset(k.ws, 0, nws));
+        SESSION_TRY(cudaMemsetAsync(k.ws, 0, nws, s->s_run));  // ordered before the first launch on the run stream
         SESSION_TRY(cudaEventCreateWithFlags(&k.uploaded, cudaEventDisableTiming));
         SESSION_TRY(cudaEventCreateWithFlags(&k.computed, cudaEventDisableTiming));
         SESSION_TRY(cudaEventCreateWithFlags(&k.downloaded, cudaEventDisableTiming));
     }
+    SESSION_TRY(cudaStreamSynchronize(s->s_run));
     return DDDM_OK;
 }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
@@ -85,6 +95,13 @@ dddm_session* dddm_session_create(int B, int m, int D, int dtype, int device) {
     s->dtype = dtype;
     s->device = device;
     s->esz = dtype == 1 ? 2 : 4;
+    s->nx = (size_t)B * m * D * s->esz;
+    s->n0 = (size_t)B * D * s->esz;
+    s->off_x0 = align_up(s->nx, 256);
+    s->off_t = s->off_x0 + align_up(s->n0, 256);
+    s->in_bytes = s->off_t + align_up((size_t)B * sizeof(float), 256);
+    s->off_out = align_up(s->nx, 256);
+    s->out_bytes = s->off_out + 256;
     if (session_alloc(s) != DDDM_OK) {
         dddm_session_destroy(s);
         return nullptr;
@@ -97,12 +114,9 @@ void dddm_session_destroy(dddm_session* s) {
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
     for (auto& k : s->slot) {
-        cudaFree(k.xhat);
-        cudaFree(k.x0);
-        cudaFree(k.grad);
-        cudaFree(k.t);
+        cudaFree(k.in);
+        cudaFree(k.outb);
         cudaFree(k.wsum);
-        cudaFree(k.out);
         cudaFree(k.ws);
         if (k.uploaded) cudaEventDestroy(k.uploaded);
         if (k.computed) cudaEventDestroy(k.computed);
@@ -121,10 +135,17 @@ int dddm_session_enqueue_host(dddm_session* s, const void* xhat_host, const void
     auto& k = s->slot[s->next % dddm_session::kSlots];
     ++s->next;
     if (k.busy) SESSION_TRY(cudaEventSynchronize(k.downloaded));  // slot's previous results have left the device
-    const size_t nx = (size_t)s->B * s->m * s->D * s->esz, n0 = (size_t)s->B * s->D * s->esz;
-    SESSION_TRY(cudaMemcpyAsync(k.xhat, xhat_host, nx, cudaMemcpyHostToDevice, s->s_in));
-    SESSION_TRY(cudaMemcpyAsync(k.x0, x0_host, n0, cudaMemcpyHostToDevice, s->s_in));
-    SESSION_TRY(cudaMemcpyAsync(k.t, t_host, (size_t)s->B * sizeof(float), cudaMemcpyHostToDevice, s->s_in));
+    const size_t nx = s->nx, n0 = s->n0;
+    const unsigned char* base = static_cast<const unsigned char*>(xhat_host);
+    if (static_cast<const unsigned char*>(x0_host) == base + s->off_x0 &&
+        reinterpret_cast<const unsigned char*>(t_host) == base + s->off_t) {
+        // the caller's buffer has the session's packed layout: one copy
+        SESSION_TRY(cudaMemcpyAsync(k.in, base, s->off_t + (size_t)s->B * sizeof(float), cudaMemcpyHostToDevice, s->s_in));
+    } else {
+        SESSION_TRY(cudaMemcpyAsync(k.xhat, xhat_host, nx, cudaMemcpyHostToDevice, s->s_in));
+        SESSION_TRY(cudaMemcpyAsync(k.x0, x0_host, n0, cudaMemcpyHostToDevice, s->s_in));
+        SESSION_TRY(cudaMemcpyAsync(k.t, t_host, (size_t)s->B * sizeof(float), cudaMemcpyHostToDevice, s->s_in));
+    }
     SESSION_TRY(cudaEventRecord(k.uploaded, s->s_in));
     SESSION_TRY(cudaStreamWaitEvent(s->s_run, k.uploaded, 0));
     int st = dddm_sigmoid_weight_sum_f32(k.t, w_bias, nullptr, k.wsum, s->B, s->s_run);
@@ -140,13 +161,28 @@ int dddm_session_enqueue_host(dddm_session* s, const void* xhat_host, const void
     if (st != DDDM_OK) return st;
     SESSION_TRY(cudaEventRecord(k.computed, s->s_run));
     SESSION_TRY(cudaStreamWaitEvent(s->s_out, k.computed, 0));
-    SESSION_TRY(cudaMemcpyAsync(out_host, k.out, 4 * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
-    if (grad_host) SESSION_TRY(cudaMemcpyAsync(grad_host, k.grad, nx, cudaMemcpyDeviceToHost, s->s_out));
+    if (grad_host && reinterpret_cast<unsigned char*>(out_host) == static_cast<unsigned char*>(grad_host) + s->off_out) {
+        SESSION_TRY(cudaMemcpyAsync(grad_host, k.outb, s->off_out + 4 * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
+    } else {
+        SESSION_TRY(cudaMemcpyAsync(out_host, k.out, 4 * sizeof(float), cudaMemcpyDeviceToHost, s->s_out));
+        if (grad_host) SESSION_TRY(cudaMemcpyAsync(grad_host, k.grad, nx, cudaMemcpyDeviceToHost, s->s_out));
+    }
     SESSION_TRY(cudaEventRecord(k.downloaded, s->s_out));
-    // No device-side edge from this step's kernels back to the upload stream: the next upload into THIS slot is three
+    // No device-side edge from this step's kernels back to the upload stream: the next upload into THIS slot is four
     // steps away and is preceded by the host-side wait on `downloaded` above (download follows compute), while the
     // next step's upload goes to another slot and may overlap these kernels.
     k.busy = true;
+    return DDDM_OK;
+}
+
+int dddm_session_packed_layout(const dddm_session* s, size_t* in_bytes, size_t* x0_offset, size_t* t_offset,
+                               size_t* out_bytes, size_t* out_offset) {
+    if (!s) return DDDM_ERR_NULL_POINTER;
+    if (in_bytes) *in_bytes = s->in_bytes;
+    if (x0_offset) *x0_offset = s->off_x0;
+    if (t_offset) *t_offset = s->off_t;
+    if (out_bytes) *out_bytes = s->out_bytes;
+    if (out_offset) *out_offset = s->off_out;
     return DDDM_OK;
 }
 

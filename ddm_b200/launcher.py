@@ -40,7 +40,11 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--data-dir", type=str, default="./data")
     p.add_argument("--out", type=str, default="./cifar10_dit_out")
     p.add_argument("--epochs", type=int, default=10)
-    p.add_argument("--batch", type=int, default=128, help="per-GPU batch")
+    p.add_argument("--batch", type=int, default=128,
+                   help="batch PER GPU when given on the command line; the `batch` key of a YAML config is the reference's "
+                        "GLOBAL batch (train_cifar10_dit.py is single-device) and is divided by the number of ranks")
+    p.add_argument("--global-batch", type=int, default=0,
+                   help="global batch, divided evenly over the ranks (overrides --batch; 0 = use --batch per GPU)")
     p.add_argument("--lr", type=float, default=1e-4)
     p.add_argument("--weight-decay", type=float, default=0.01)
     p.add_argument("--beta", type=float, default=0.1)
@@ -60,6 +64,21 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--sample-batch", type=int, default=64)
     p.add_argument("--sample-steps", type=int, default=20)
     p.add_argument("--eps-churn", type=float, default=1.0)
+    # reference flags kept so that its command lines and configs/cifar10_dit.yaml load unchanged
+    # (train_cifar10_dit.py:376-395); evaluation with Inception features, W&B and the CPU data-loader workers are outside
+    # the hot path: the values are accepted, recorded in the checkpoint config, and reported as ignored at start-up
+    p.add_argument("--device", type=str, default="cuda", help="must be a CUDA device (there is no CPU path)")
+    p.add_argument("--workers", type=int, default=4)
+    p.add_argument("--no-augment", action="store_true")
+    p.add_argument("--eval-every", type=int, default=0)
+    p.add_argument("--eval-batch", type=int, default=256)
+    p.add_argument("--eval-samples", type=int, default=1024)
+    p.add_argument("--fid-samples", type=int, default=10000)
+    p.add_argument("--mmd-samples", type=int, default=2048)
+    p.add_argument("--mmd-sigma", type=float, default=1.0)
+    p.add_argument("--wandb", action="store_true")
+    p.add_argument("--wandb-project", type=str, default="dddm")
+    p.add_argument("--wandb-name", type=str, default=None)
     # launcher-only flags
     p.add_argument("--synthetic", action="store_true", help="CIFAR-shaped random images resident on the GPU (no dataset)")
     p.add_argument("--steps-per-epoch", type=int, default=100, help="with --synthetic")
@@ -85,8 +104,33 @@ def apply_yaml(parser: argparse.ArgumentParser, args: argparse.Namespace) -> Non
         dest = key.replace("-", "_")
         if not hasattr(args, dest):
             raise ValueError(f"Unknown config key: {key}")
+        if dest == "batch":  # the reference's batch is the global one (App. D.1: 256 = 4 x 64)
+            if args.global_batch == 0 and args.batch == parser.get_default("batch"):
+                args.global_batch = int(value)
+            continue
         if getattr(args, dest) == parser.get_default(dest):
             setattr(args, dest, value)
+
+
+IGNORED_REFERENCE_FLAGS = ("eval_every", "eval_batch", "eval_samples", "fid_samples", "mmd_samples", "mmd_sigma", "wandb",
+                           "wandb_project", "wandb_name")
+
+
+def resolve_batch(args: argparse.Namespace, world: int) -> list:
+    """Per-GPU batch from --global-batch / YAML `batch`; returns the notices to print on rank 0."""
+    notes = []
+    if not str(args.device).startswith("cuda"):
+        raise ValueError(f"--device {args.device}: the launcher runs on CUDA devices only (one process per GPU)")
+    if args.global_batch:
+        if args.global_batch % world:
+            raise ValueError(f"global batch {args.global_batch} is not divisible by {world} ranks")
+        args.batch = args.global_batch // world
+        notes.append(f"global batch {args.global_batch} -> {args.batch} per GPU on {world} rank(s)")
+    if args.eval_every or args.wandb:
+        notes.append("evaluation (FID / image MMD) and W&B logging are outside this launcher: --eval-* / --fid-* / "
+                     "--mmd-* / --wandb* are accepted and ignored (ddm_b200.rbf_mmd2 and sample_dddm_sharded are the "
+                     "evaluation-side kernels)")
+    return notes
 
 
 def init_distributed():
@@ -337,6 +381,9 @@ def main(argv=None) -> None:
     if args.m < 2:
         parser.error("m must be >= 2 for the generalized energy score")
     world, rank, dev = init_distributed()
+    for note in resolve_batch(args, world):
+        if rank == 0:
+            print(f"[ddm_b200.launcher] {note}", flush=True)
     os.makedirs(args.out, exist_ok=True)
     tr = Trainer(args, dev, world)
 
@@ -346,12 +393,12 @@ def main(argv=None) -> None:
             from torchvision import datasets, transforms
         except ImportError as exc:
             raise RuntimeError("torchvision is needed for CIFAR-10; pass --synthetic to train on random images") from exc
-        tf = transforms.Compose([transforms.RandomCrop(args.image_size, padding=4), transforms.RandomHorizontalFlip(),
-                                 transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
+        aug = [] if args.no_augment else [transforms.RandomCrop(args.image_size, padding=4), transforms.RandomHorizontalFlip()]
+        tf = transforms.Compose(aug + [transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
         ds = datasets.CIFAR10(args.data_dir, train=True, download=False, transform=tf)
         sampler = torch.utils.data.distributed.DistributedSampler(ds) if world > 1 else None
         loader = torch.utils.data.DataLoader(ds, batch_size=args.batch, sampler=sampler, shuffle=sampler is None,
-                                             num_workers=4, pin_memory=True, drop_last=True)
+                                             num_workers=args.workers, pin_memory=True, drop_last=True)
 
     history, gstep = [], 0
     for epoch in range(1, args.epochs + 1):

@@ -64,9 +64,15 @@ def energy_fused(xhat: Tensor, x0: Tensor, weight: Tensor, weight_scale: float, 
     _require_cuda(xhat, x0, weight)
     if xhat.dim() != 3 or x0.dim() != 2 or x0.shape[0] != xhat.shape[0] or x0.shape[1] != xhat.shape[2]:
         raise ValueError(f"expected xhat [B,m,D] and x0 [B,D], got {tuple(xhat.shape)} and {tuple(x0.shape)}")
-    if x0.dtype != xhat.dtype:
-        raise TypeError("xhat and x0 must have the same dtype")
     sfx = _suffix(xhat)
+    if x0.dtype != xhat.dtype:
+        # mixed entry point: bf16 draws (as a bf16 backbone wrote them) against fp32 data, bf16 gradient out
+        if not (xhat.dtype == torch.bfloat16 and x0.dtype == torch.float32):
+            raise TypeError("xhat and x0 must have the same dtype (or bf16 xhat with fp32 x0)")
+        if not _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(xhat.shape[1], xhat.shape[2]):
+            raise TypeError(f"bf16 xhat with fp32 x0 is not covered for m={xhat.shape[1]}, D={xhat.shape[2]}: "
+                            "pass both in one dtype")
+        sfx = "bf16_x0f32"
     xhat, x0 = xhat.contiguous(), x0.contiguous()
     weight = weight.reshape(-1)[:1].float().contiguous()
     B, m, D = xhat.shape
@@ -131,9 +137,15 @@ def energy_terms_fwd(xhat: Tensor, x0: Tensor, beta: float) -> Tuple[Tensor, Ten
     _require_cuda(xhat, x0)
     if xhat.dim() != 3 or x0.dim() != 2 or x0.shape[0] != xhat.shape[0] or x0.shape[1] != xhat.shape[2]:
         raise ValueError(f"expected xhat [B,m,D] and x0 [B,D], got {tuple(xhat.shape)} and {tuple(x0.shape)}")
-    if x0.dtype != xhat.dtype:
-        raise TypeError("xhat and x0 must have the same dtype")
     sfx = _suffix(xhat)
+    if x0.dtype != xhat.dtype:
+        # mixed entry point: bf16 draws (as a bf16 backbone wrote them) against fp32 data, bf16 gradient out
+        if not (xhat.dtype == torch.bfloat16 and x0.dtype == torch.float32):
+            raise TypeError("xhat and x0 must have the same dtype (or bf16 xhat with fp32 x0)")
+        if not _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(xhat.shape[1], xhat.shape[2]):
+            raise TypeError(f"bf16 xhat with fp32 x0 is not covered for m={xhat.shape[1]}, D={xhat.shape[2]}: "
+                            "pass both in one dtype")
+        sfx = "bf16_x0f32"
     xhat, x0 = xhat.contiguous(), x0.contiguous()
     B, m, D = xhat.shape
     out = torch.empty(2, dtype=torch.float32, device=xhat.device)

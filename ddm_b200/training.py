@@ -7,7 +7,7 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import _cabi, ops
 
 _KEYS = ("loss", "confidence", "interaction", "weight")
 
@@ -159,9 +159,16 @@ def distributional_training_step(
         loss = weight * (conf - (lam / (2.0 * (m - 1))) * inter)
         packed = torch.stack([loss.detach().float(), conf.detach().float(), inter.detach().float(), weight.float()])
     else:
-        packed, _ = ops.energy_fused(x0hat.reshape(batch, m, -1).to(dtype),
-                                     x0_flat if x0_flat is not None else x0.reshape(batch, -1), w_sum,
-                                     weight_scale, float(beta), float(lam), want_grad)
+        xh = x0hat.reshape(batch, m, -1)
+        x0_2d = x0_flat if x0_flat is not None else x0.reshape(batch, -1)
+        if xh.dtype != x0_2d.dtype:
+            # a bf16 backbone under fp32 data: hand K1 the draws as they are (mixed entry point) instead of
+            # up-converting them — one pass over xhat and one over the gradient less
+            mixed = (xh.dtype == torch.bfloat16 and x0_2d.dtype == torch.float32 and
+                     bool(_cabi.lib().dddm_energy_fused_bf16_x0f32_supported(m, xh.shape[2])))
+            if not mixed:
+                xh = xh.to(dtype)
+        packed, _ = ops.energy_fused(xh, x0_2d, w_sum, weight_scale, float(beta), float(lam), want_grad)
         loss = packed[0].to(dtype)
         packed = packed.detach()
 

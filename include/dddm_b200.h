@@ -11,8 +11,11 @@
  *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
  *   - all data pointers are DEVICE pointers owned by the caller unless the name says `_host`;
  *     nothing is allocated or freed inside (except by the explicit dddm_session_* objects);
- *   - every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*),
- *     re-entrant, and never throws: it returns 0 or a negative dddm_status / positive cudaError_t;
+ *   - every call is asynchronous on `stream` (a cudaStream_t / CUstream passed as void*), acts on the CURRENT
+ *     device (host-side caches are keyed by device, so one process may drive several GPUs), may be called from
+ *     several threads at once, and never throws: it returns 0 or a negative dddm_status / positive cudaError_t.
+ *     The one exception is dddm_set_tuning / dddm_set_trace_buffer below: they change PROCESS-GLOBAL state read by
+ *     later launches and are meant for benchmarks and tests on a quiescent library, not for concurrent use;
  *   - `bf16` data is raw uint16 storage of IEEE bfloat16; accumulation is always fp32;
  *   - scalars produced on the device stay on the device (no hidden host synchronisation).
  */
@@ -78,6 +81,16 @@ int dddm_energy_fused_f32(const float* xhat, const float* x0, const float* weigh
 int dddm_energy_fused_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* weight_dev,
                            float weight_scale, dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m,
                            int D, float beta, float lam, dddm_stream_t stream);
+/*
+ * Mixed entry point for a bf16 backbone (dddm/training.py:75-85 under autocast): the draws arrive in bf16 as the
+ * backbone wrote them, the data x0 stays fp32 (not rounded), the gradient leaves in bf16 — no up-conversion pass
+ * over xhat and no down-conversion pass over the gradient.  m <= 8 and rows of 16-byte multiples (D % 8 == 0);
+ * dddm_energy_fused_bf16_x0f32_supported(m, D) tells whether a shape is covered (else DDDM_ERR_UNSUPPORTED).
+ */
+int dddm_energy_fused_bf16_x0f32(const dddm_bf16* xhat, const float* x0, const float* weight_dev, float weight_scale,
+                                 dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
+                                 float lam, dddm_stream_t stream);
+int dddm_energy_fused_bf16_x0f32_supported(int m, int D);
 
 /*
  * K1b — the API-faithful split pair behind generalized_energy_terms(x0hats, x0, beta, lam)
@@ -172,6 +185,12 @@ int dddm_session_step_host(dddm_session*, const void* xhat_host, const void* x0_
 int dddm_session_enqueue_host(dddm_session*, const void* xhat_host, const void* x0_host, const float* t_host,
                               float w_bias, float beta, float lam, void* grad_host, float* out_host);
 int dddm_session_wait(dddm_session*);
+/* Packed host layout: when the caller keeps a step's inputs in ONE host buffer [xhat | x0 | t] with x0 at
+ * `x0_offset` and t at `t_offset` (in_bytes total), and its outputs in one buffer [grad | out[4]] with out at
+ * `out_offset` (out_bytes total), dddm_session_enqueue_host recognises the pointers and issues exactly one copy per
+ * direction.  Any argument may be NULL. */
+int dddm_session_packed_layout(const dddm_session*, size_t* in_bytes, size_t* x0_offset, size_t* t_offset,
+                               size_t* out_bytes, size_t* out_offset);
 void* dddm_host_alloc(size_t bytes); /* pinned host memory */
 void dddm_host_free(void*);
 int dddm_last_error(void);
@@ -219,7 +238,12 @@ int dddm_rbf_kernel_sum_f32(const float* G, long ldg, const float* a2, const flo
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
  *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto),
  *         "energy.threads" (threads per CTA of variant 3, 0 = auto), "energy.nv" (16-byte vectors per
- *         thread of variant 1, 0 = auto), "energy.pdl" (programmatic dependent launch, default 1), "energy.ctas" (experiment).
+ *         thread of variant 1, 0 = auto), "energy.pdl" (programmatic dependent launch, default 1), "energy.ctas" (experiment),
+ *         "energy.variant" = 5 (single-wave register-resident kernel for m <= 8: "energy.threads" 128/256/384 x "energy.nv"
+ *         1..3 vectors per thread), "energy.loader" (TMA-staged kernel: 0/1 TMA bulk copies, 2 cp.async commit groups with
+ *         "energy.window" chunks in flight), "energy.ldhint" / "energy.sthint" (L2 eviction priority of the single-wave
+ *         kernel's loads / stores: 0 normal, 1 first, 2 last, 3 unchanged), "energy.nostore" (diagnostics).
+ * Process-global and NOT thread-safe: set them while no other thread is launching.
  * dddm_launch_count returns the number of kernels this library has launched in this process.
  * ------------------------------------------------------------------------------------------ */
 int dddm_set_tuning(const char* key, int value);

@@ -175,6 +175,31 @@ def test_ragged_shapes(dev, m, D):
     _check_case(xh.numpy(), x0.numpy(), 0.1, dev, dtype=torch.bfloat16, rel=BF16_REL)
 
 
+@pytest.mark.parametrize("B,m,D,regime,beta", [(128, 8, 3072, "late", 0.1), (128, 8, 3072, "early", 1.0), (5, 3, 40, "late", 2.0),
+                                               (9, 8, 12288, "late", 0.1), (3, 5, 4104, "early", 0.1), (300, 8, 1024, "late", 1.0)])
+def test_mixed_bf16_draws_fp32_data(dev, B, m, D, regime, beta):
+    """Mixed entry point (bf16 xhat as a bf16 backbone writes it, fp32 x0, bf16 gradient): against the fp64 oracle on
+    the bf16-rounded draws and the EXACT fp32 data — and strictly closer to it than the all-bf16 entry, which rounds x0."""
+    from ddm_b200 import _cabi
+
+    assert _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(m, D) == 1
+    xh, x0 = _synthetic(B, m, D, regime, seed=B + m)
+    xh, x0 = xh.to(dev).to(torch.bfloat16), x0.to(dev)
+    loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(), beta, 1.3, 0.7)
+    out, g = _fused(xh, x0, 0.7, beta, 1.3)
+    assert g.shape == tuple(xh.shape)
+    scale = max(abs(conf), abs(inter))
+    assert abs(out[1] - conf) <= FP32_REL * scale and abs(out[2] - inter) <= FP32_REL * scale  # values are fp32-exact
+    assert abs(out[0] - loss) <= 2 * FP32_REL * 0.7 * scale
+    assert _rel(g, grad) <= BF16_REL  # the gradient is rounded to bf16 on the way out
+    if regime == "late" and D >= 1024:  # rounding x0 to bf16 (|x0| <= 1, draws 0.05 away) visibly moves the terms
+        out_b, _ = _fused(xh, x0.to(torch.bfloat16), 0.7, beta, 1.3)
+        assert abs(out_b[1] - conf) > 10 * abs(out[1] - conf)
+    assert _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(16, 3072) == 0
+    with pytest.raises(TypeError):
+        _fused(xh.float(), x0.to(torch.bfloat16), 0.7, beta, 1.3)
+
+
 def test_wave_kernel_plans(dev):
     """The single-wave register-resident kernel (variant 5, the path one launch of B <= #SMs rows takes): every
     (threads, vectors per thread, coefficient placement) plan, fp32 and bf16, m = 2..8, rows that do not fill the

@@ -245,6 +245,22 @@ def test_host_session_matches_device_path(dev):
                                                         None, o.data_ptr()))
             _cabi.check(L.dddm_session_wait(s))
             assert all(torch.equal(o, out) for o in outs)
+            # packed host layout: [xhat | x0 | t] and [grad | out] in ONE pinned buffer each -> one copy per direction
+            sz = [ctypes.c_size_t() for _ in range(5)]
+            _cabi.check(L.dddm_session_packed_layout(s, *[ctypes.addressof(v) for v in sz]))
+            in_bytes, x0_off, t_off, out_bytes, out_off = [int(v.value) for v in sz]
+            assert x0_off >= a.numel() * a.element_size() and t_off >= x0_off + c.numel() * c.element_size()
+            assert x0_off % 256 == 0 and t_off % 256 == 0 and out_off % 256 == 0 and in_bytes >= t_off + 4 * B
+            pin, pout = torch.zeros(in_bytes, dtype=torch.uint8).pin_memory(), torch.zeros(out_bytes, dtype=torch.uint8).pin_memory()
+            pin[:a.numel() * a.element_size()] = a.view(torch.uint8).reshape(-1)
+            pin[x0_off:x0_off + c.numel() * c.element_size()] = c.view(torch.uint8).reshape(-1)
+            pin[t_off:t_off + 4 * B] = t.view(torch.uint8).reshape(-1)
+            for _ in range(6):
+                _cabi.check(L.dddm_session_enqueue_host(s, pin.data_ptr(), pin.data_ptr() + x0_off, pin.data_ptr() + t_off,
+                                                        0.2, 0.1, 1.0, pout.data_ptr(), pout.data_ptr() + out_off))
+            _cabi.check(L.dddm_session_wait(s))
+            assert torch.equal(pout[out_off:out_off + 16].view(torch.float32), out)
+            assert torch.equal(pout[:a.numel() * a.element_size()].view(dtype).reshape(a.shape), gout)
         finally:
             L.dddm_session_destroy(s)
     assert not L.dddm_session_create(0, 8, 4, 0, 0) and L.dddm_last_error() == -2
@@ -451,3 +467,39 @@ def test_trainer_cuda_graph_equals_eager(dev, monkeypatch):
                 assert rel <= tol, (precision, mode, rel)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
+
+
+def test_second_device_in_one_process(dev):
+    """Host-side caches (shared-memory opt-in, SM count) are per device: a process that used GPU 0 can run the
+    110 KB-tile kernels on GPU 1 — through the custom ops and through a host session."""
+    from ddm_b200 import _cabi, ops
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L = _cabi.lib()
+    gen = torch.Generator().manual_seed(11)
+    x0 = torch.randn(16, 3072, generator=gen).clamp(-1, 1)
+    xh = x0[:, None] + 0.05 * torch.randn(16, 8, 3072, generator=gen)
+    res = []
+    for d in (0, 1, 0):
+        device = torch.device("cuda", d)
+        w = torch.tensor([8.0], device=device)
+        out, grad = ops.energy_fused(xh.to(device), x0.to(device), w, 1.0 / 16, 0.1, 1.0, True)
+        o32, g32 = ops.energy_fused(xh.to(device).repeat(1, 4, 1), x0.to(device), w, 1.0 / 16, 0.1, 1.0, True)  # m = 32: blocked kernel
+        torch.cuda.synchronize(device)
+        res.append((out.cpu(), grad.cpu(), o32.cpu(), g32.cpu()))
+    for r in res[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(res[0], r))
+    t = torch.rand(16, generator=gen)
+    hx, h0, ht = xh.contiguous().pin_memory(), x0.pin_memory(), t.pin_memory()
+    outs = []
+    for d in (0, 1):
+        s = L.dddm_session_create(16, 8, 3072, 0, d)
+        assert s
+        o = torch.empty(4).pin_memory()
+        _cabi.check(L.dddm_session_step_host(s, hx.data_ptr(), h0.data_ptr(), ht.data_ptr(), 0.0, 0.1, 1.0, None,
+                                             o.data_ptr()))
+        L.dddm_session_destroy(s)
+        outs.append(o.clone())
+    assert torch.equal(outs[0], outs[1])
+    torch.cuda.set_device(dev)
