@@ -194,7 +194,7 @@ def run_reference(args) -> None:
     w = torch_port.sigmoid_weight(t, W_BIAS).mean()
     # bounded: each step is ~0.1-0.3 s of CPU work; cap the whole run at a few minutes
     steps = max(1, min(args.steps, 200))
-    warmup = max(1, min(args.warmup, 3))
+    warmup = max(3, min(args.warmup, 20))  # the driver's W is honoured (each CPU step is ~40 ms: 20 of them stay bounded)
     for _ in range(warmup):
         torch_port.energy_fwd_bwd(xh, x0, w, BETA, LAM)
     t0 = time.perf_counter()
@@ -206,7 +206,10 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name("f32"), "device": "host CPU", "threads": torch.get_num_threads()},
+        "config": {"workload": workload_name("f32"), "rows_per_gpu": B, "global_rows": B,
+                   "parallelism": "host CPU (rank 0 only)", "l2_policy": "n/a (CPU)",
+                   "launch": f"eager PyTorch + autograd on {torch.get_num_threads()} host threads",
+                   "timed_region": f"exactly {steps} steps, wall clock", "kernel": "oracle/torch_port.py", "tuning": "n/a"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{steps} full fwd+bwd passes over the B={B} batch (oracle/torch_port.py, eager "
                                    f"PyTorch + autograd as in the reference), os.cpu_count()={os.cpu_count()}"},
@@ -216,19 +219,102 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def run_aux(args, dev, world) -> dict:
-    """Auxiliary, outside the timed region: BASELINE configs 4 (DP DiT training img/s) and 5 (Algorithm-2 sampler)."""
+AUX_PARTIAL: dict = {}  # what run_aux has finished so far (reported if its watchdog fires)
+
+
+def run_aux(args, dev, world, rank, L, peak) -> dict:
+    """Auxiliary, outside the timed region: the other dtype of BASELINE config 2, the elementwise kernels' rooflines,
+    BASELINE configs 4 (DP DiT training img/s, + multi-rank parity on hardware) and 5 (Algorithm-2 sampler), rbf_mmd2."""
     import torch
     import torch.distributed as dist
 
-    aux = {}
+    from ddm_b200 import _cabi
+
+    aux = AUX_PARTIAL
+
+    # -- BASELINE config 2, second half: the same isolated loss in bf16 (all-bf16 and the mixed bf16-draws/fp32-data entry)
+    def k1_block(dtype_name, x0_f32=False):
+        kb = K1Bench(L, dev, dtype_name, rank, world, args.streams, args.no_graph, x0_f32=x0_f32)
+        K = 480
+        with torch.cuda.stream(kb.stream):
+            kb.run_serial(K)
+            kb.run_multi(K)
+            kb.stream.synchronize()
+            ser, _ = kb.timed(kb.run_serial, K, 5)
+            mul, _ = kb.timed(kb.run_multi, K, 3)
+        if world > 1:
+            tt = torch.tensor([ser, mul], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ser, mul = float(tt[0]), float(tt[1])
+        ach, ach_m = kb.algo_bytes / (ser / K) / 1e9, kb.algo_bytes / (mul / K) / 1e9
+        sfx = "bf16" if dtype_name == "bf16" else "f32"
+        return {"rows_per_s": world * B * K / ser, "ms_per_step": 1e3 * ser / K,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "algorithmic_bytes_per_launch": kb.algo_bytes},
+                "single_stream_frac": ach / peak,
+                "multi_stream": {"streams": kb.nstreams, "ms_per_step": 1e3 * mul / K, "rows_per_s": world * B * K / mul,
+                                 "frac": ach_m / peak},
+                "kernel": _cabi.describe_energy(B, M, D, sfx), "x0": "fp32 (mixed entry point)" if x0_f32 else sfx,
+                "timed_region": f"median of 5 repetitions of exactly {K} single-stream steps, {kb.nsets} rotating sets"}
+
+    other = "bf16" if args.dtype == "f32" else "f32"
+    aux[f"k1_{other}"] = k1_block(other)
+    aux["k1_bf16_x0f32"] = k1_block("bf16", x0_f32=True)
+    torch.cuda.empty_cache()
+
+    if not args.no_elementwise and world == 1:
+        aux["elementwise"] = elementwise_rooflines(dev, peak)
+
+    precisions = [p for p in args.dit_precision.split(",") if p in ("bf16", "tf32", "fp32")]
     if args.dit_steps > 0:
         from ddm_b200 import launcher
 
-        targs = launcher.build_parser().parse_args(["--synthetic", "--precision", args.dit_precision])
-        aux["dit_train"] = launcher.measure_throughput(targs, dev, world, steps=args.dit_steps, warmup=3)
-        aux["dit_train"]["config"] = ("DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
-                                      "data-parallel (one flat-gradient NCCL all-reduce), loss kernels K4+K2c+K1")
+        aux["dit_train"] = {"config": "DDDMDiT CIFAR-10 32x32 training step on synthetic images, batch 128/GPU, m=8, "
+                                      "data-parallel (one flat-gradient NCCL all-reduce), loss kernels K4+K2c+K1"}
+        for prec in precisions:
+            steps = args.dit_steps if prec == "bf16" else max(20, args.dit_steps // 2)
+            targs = launcher.build_parser().parse_args(["--synthetic", "--precision", prec])
+            aux["dit_train"][prec] = launcher.measure_throughput(targs, dev, world, steps=steps, warmup=5)
+            torch.cuda.empty_cache()
+        first = aux["dit_train"].get(precisions[0]) if precisions else None
+        if first:  # the keys earlier rounds' readers look for
+            aux["dit_train"].update({k: first[k] for k in ("img_per_s", "ms_per_step", "steps", "precision", "n_gpus")})
+        # multi-rank parity on hardware (also run at N = 1: one graph against the eager global step)
+        pargs = launcher.build_parser().parse_args(["--synthetic", "--precision", "fp32"])
+        aux["dp_parity"] = launcher.dp_parity(pargs, dev, world)
+        pargs = launcher.build_parser().parse_args(["--synthetic", "--precision", "bf16"])
+        aux["dp_parity_bf16"] = launcher.dp_parity(pargs, dev, world)
+        torch.cuda.empty_cache()
+    if world > 1:
+        # the isolated loss WITH its one data-path collective in the timed region: K4 -> all-reduce(sum_b w) -> K1, eager,
+        # one stream.  Dominated by the latency of a 4-byte NCCL all-reduce; in training it hides behind the backbone.
+        kb = K1Bench(L, dev, args.dtype, rank, world, 1, True, nsets=8)
+        tdev = [torch.rand(B, device=dev) for _ in range(8)]
+        wsum = [torch.empty(1, device=dev) for _ in range(8)]
+
+        def step(i):
+            s = kb.sets[i % 8]
+            _cabi.check(L.dddm_sigmoid_weight_sum_f32(tdev[i % 8].data_ptr(), W_BIAS, None, s["wsum"].data_ptr(), B,
+                                                      torch.cuda.current_stream().cuda_stream))
+            dist.all_reduce(s["wsum"])
+            kb.launch(s, torch.cuda.current_stream().cuda_stream)
+
+        for i in range(10):
+            step(i)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 100
+        for i in range(n):
+            step(i)
+        e1.record()
+        e1.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        aux["k1_with_weight_allreduce"] = {"ms_per_step": 1e3 * float(tt) / n, "rows_per_s": world * B * n / float(tt),
+                                           "steps": n, "launch": "eager: K4, NCCL all-reduce of one float, K1 on one stream"}
+        del wsum
     if args.dit_steps > 0 and world == 1 and args.cpu_seconds > 0:
         # CPU baseline of config 4 at a REDUCED batch (SURVEY.md §8d: a full B=128 CPU step is ~5.7 TFLOP): the
         # reference's step (oracle/torch_port.training_step = dddm/training.py:57-85) + backward + clip + AdamW on the
@@ -265,7 +351,7 @@ def run_aux(args, dev, world) -> dict:
 
         per = max(1, args.sampler_samples // world)
         net = DDDMDiT().to(dev)
-        if args.dit_precision == "bf16":
+        if "bf16" in precisions or not precisions:
             net = net.to(torch.bfloat16)  # bf16 weights and activations; x_t, the noise and the K3 update stay fp32
         res = {}
         if True:
@@ -327,6 +413,195 @@ def run_aux(args, dev, world) -> dict:
     return aux
 
 
+class K1Bench:
+    """The isolated fused loss on rotating HBM-cold buffer sets, timed two ways: strictly serialized on ONE stream
+    (the headline: what a training step sees, one loss launch between the backbone's forward and backward) and with
+    the independent steps issued round-robin on several streams (aggregate: consecutive minibatches overlap)."""
+
+    def __init__(self, L, dev, dtype_name, rank, world, nstreams, no_graph, nsets=0, x0_f32=False):
+        import torch
+        import torch.distributed as dist
+
+        from ddm_b200 import _cabi
+
+        self.torch, self.L, self.dev, self.world = torch, L, dev, world
+        self.dtype_name = dtype_name
+        tdtype = torch.float32 if dtype_name == "f32" else torch.bfloat16
+        esz = 4 if dtype_name == "f32" else 2
+        self.algo_bytes = (2 * B * M * D) * esz + B * D * (4 if x0_f32 else esz)  # SURVEY.md §8(d): read xhat + x0, write grad
+        self.nsets = nsets or max(4, -(-8 * L2_BYTES // self.algo_bytes))  # working set > 8x L2: every launch reads HBM-cold data
+        fn = getattr(L, f"dddm_energy_fused_{dtype_name}" + ("_x0f32" if x0_f32 else ""))
+        self.sets = []
+        for s in range(self.nsets):
+            xh, x0, t = make_inputs(1000 * rank + s, tdtype)
+            if x0_f32:
+                x0 = make_inputs(1000 * rank + s, torch.float32)[1]
+            self.sets.append({"xh": xh.to(dev), "x0": x0.to(dev), "t": t.to(dev),
+                              "grad": torch.empty(B, M, D, dtype=tdtype, device=dev), "out": torch.zeros(4, device=dev),
+                              "wsum": torch.empty(1, device=dev),
+                              "ws": torch.zeros(L.dddm_energy_workspace_bytes(B, M), dtype=torch.uint8, device=dev)})
+        self.stream = torch.cuda.Stream(dev)
+        with torch.cuda.stream(self.stream):
+            for s in self.sets:  # W = mean_b w(t_b): an input of the isolated loss, computed once outside the timed region
+                _cabi.check(L.dddm_sigmoid_weight_sum_f32(s["t"].data_ptr(), W_BIAS, None, s["wsum"].data_ptr(), B,
+                                                          self.stream.cuda_stream))
+            if world > 1:  # global-batch weight (SURVEY.md §8e): one float all-reduce, outside the timed region
+                for s in self.sets:
+                    dist.all_reduce(s["wsum"])
+        self.stream.synchronize()
+        wscale = 1.0 / (B * world)
+
+        def launch(s, cuda_stream):
+            _cabi.check(fn(s["xh"].data_ptr(), s["x0"].data_ptr(), s["wsum"].data_ptr(), wscale, s["grad"].data_ptr(),
+                           s["out"].data_ptr(), s["ws"].data_ptr(), B, M, D, BETA, LAM, cuda_stream))
+
+        self.launch = launch
+        self.no_graph = no_graph
+        self.nstreams = 1 if no_graph else max(1, nstreams)
+        self.run_serial = self._runner(1)
+        self.run_multi = self._runner(self.nstreams) if self.nstreams > 1 else self.run_serial
+
+    def _runner(self, nstreams):
+        torch, dev, stream, sets, nsets = self.torch, self.dev, self.stream, self.sets, self.nsets
+        sides = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
+
+        def capture(n):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                main = torch.cuda.current_stream()
+                for sd in sides:
+                    sd.wait_stream(main)
+                for i in range(n):
+                    st = main if i % nstreams == 0 else sides[i % nstreams - 1]
+                    self.launch(sets[i % nsets], st.cuda_stream)
+                for sd in sides:
+                    main.wait_stream(sd)
+            return g
+
+        if self.no_graph:
+            def run_plain(n):
+                for i in range(n):
+                    self.launch(sets[i % nsets], stream.cuda_stream)
+            return run_plain
+        chunk = nsets * max(1, 480 // nsets)
+        graphs = {}
+
+        def run_graph(n):
+            full, rem = divmod(n, chunk)
+            for size, count in ((chunk, full), (rem, 1 if rem else 0)):
+                if count:
+                    if size not in graphs:
+                        graphs[size] = capture(size)
+                    for _ in range(count):
+                        graphs[size].replay()
+        return run_graph
+
+    def timed(self, runner, K, reps):
+        """Median over `reps` repetitions of EXACTLY K steps between two CUDA events on the launch stream."""
+        torch = self.torch
+        times = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            runner(K)
+            e1.record(self.stream)
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e-3)
+        return sorted(times)[len(times) // 2], times
+
+
+def copy_ceiling(dev, h2d_bytes, d2h_bytes, reps=20):
+    """Plain pinned-memory copies of one step's bytes, no kernels: H2D alone, D2H alone, both directions at once (two
+    streams).  The ceiling the host-buffer e2e figure is measured against — a number for "PCIe/host limited"."""
+    import torch
+
+    hin, hout = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory(), torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    din, dout = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev), torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(up, down):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    run(True, True)
+    t_up, t_down, t_both = run(True, False), run(False, True), run(True, True)
+    return {"h2d_gbs": h2d_bytes / t_up / 1e9, "d2h_gbs": d2h_bytes / t_down / 1e9,
+            "duplex_h2d_gbs": h2d_bytes / t_both / 1e9, "duplex_d2h_gbs": d2h_bytes / t_both / 1e9,
+            "duplex_s_per_step": t_both, "bytes": [h2d_bytes, d2h_bytes],
+            "how": f"{reps} back-to-back cudaMemcpyAsync of one step's bytes per direction from/to pinned host memory, "
+                   "two streams, wall clock around a device synchronize"}
+
+
+def elementwise_rooflines(dev, peak):
+    """K2 / K2c / K3 at their BASELINE shapes, same discipline as K1: rotating buffers beyond 8x L2, one stream, CUDA
+    graph of back-to-back launches, CUDA events."""
+    import torch
+
+    from ddm_b200 import ops
+
+    res = {}
+    C, H, Wd = 3, 32, 32
+
+    def bench(name, make, call, nbytes):
+        nsets = max(4, -(-8 * L2_BYTES // nbytes))
+        sets = [make(i) for i in range(nsets)]
+        stream = torch.cuda.Stream(dev)
+        with torch.cuda.stream(stream):
+            for s_ in sets[:3]:
+                call(s_)
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for s_ in sets:
+                call(s_)
+        ts = []
+        with torch.cuda.stream(stream):
+            g.replay()
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                g.replay()
+                e1.record(stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e-3 / nsets)
+        sec = sorted(ts)[2]
+        res[name] = {"us_per_launch": sec * 1e6, "algorithmic_bytes": nbytes,
+                     "roofline": {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": nbytes / sec / 1e9 / peak}, "rotating_sets": nsets}
+        del sets, g
+        torch.cuda.empty_cache()
+
+    bench("K2_forward_marginal_expand_f32",
+          lambda i: (torch.rand(B, C, H, Wd, device=dev), torch.rand(B, device=dev), torch.randn(B, C, H, Wd, device=dev)),
+          lambda s_: ops.forward_marginal_expand(s_[0], s_[1], s_[2], M, False), (2 * B * D + B * M * D) * 4 + 4 * B)
+    bench("K2c_forward_marginal_concat_f32_to_bf16",
+          lambda i: (torch.rand(B, C, H, Wd, device=dev), torch.rand(B, device=dev), torch.randn(B, C, H, Wd, device=dev),
+                     torch.randn(B, M, C, H, Wd, device=dev)),
+          lambda s_: ops.forward_marginal_concat(s_[0], s_[1], s_[2], s_[3], True, 4),
+          (2 * B * D + B * M * D) * 4 + 2 * B * M * D * 2 + B * D * 4)
+    n = 1024
+    bench("K3_bridge_step_f32_1024",
+          lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
+                     torch.randn(n, C, H, Wd, device=dev), torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
+          lambda s_: ops.bridge_step(s_[0], s_[1], s_[2], s_[3], s_[4], 1.0), 4 * n * D * 4)
+    if hasattr(ops, "bridge_step_rng"):
+        bench("K3_bridge_step_fused_noise_f32_1024",
+              lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
+                         torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
+              lambda s_: ops.bridge_step_rng(s_[0], s_[1], s_[2], s_[3], 1.0), 3 * n * D * 4)
+    return res
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -339,14 +614,16 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of CUDA graphs")
     ap.add_argument("--sets", type=int, default=0, help="rotating input sets (0 = enough to exceed 8x L2)")
     ap.add_argument("--streams", type=int, default=6,
-                    help="streams the independent steps are issued on round-robin inside the CUDA graph (1 = serialized)")
+                    help="streams of the AGGREGATE figure (independent steps round-robin inside one CUDA graph); the headline "
+                         "value is always the single-stream one")
     ap.add_argument("--tune", default="", help="comma list key=value for dddm_set_tuning, e.g. energy.cluster=4")
-    ap.add_argument("--dit-steps", type=int, default=10,
+    ap.add_argument("--dit-steps", type=int, default=100,
                     help="auxiliary: DP DiT training steps to time for the img/s figure (0 = skip)")
-    ap.add_argument("--dit-precision", default="bf16", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--dit-precision", default="bf16,tf32,fp32", help="comma list of backbone precisions to time")
     ap.add_argument("--sampler-samples", type=int, default=1024, help="auxiliary: Algorithm-2 samples (0 = skip)")
     ap.add_argument("--mmd-samples", type=int, default=10000, help="auxiliary: rbf_mmd2 set size (0 = skip)")
-    ap.add_argument("--aux-timeout", type=float, default=240.0, help="seconds the auxiliary measurements may take")
+    ap.add_argument("--no-elementwise", action="store_true", help="skip the K2/K2c/K3 rooflines")
+    ap.add_argument("--aux-timeout", type=float, default=420.0, help="seconds the auxiliary measurements may take")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -374,135 +651,76 @@ def main() -> None:
 
     tdtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     esz = 4 if args.dtype == "f32" else 2
-    algo_bytes = (2 * B * M * D + B * D) * esz  # read xhat + x0, write grad
-    nsets = args.sets or max(4, -(-8 * L2_BYTES // algo_bytes))  # working set > 8x L2: every launch reads HBM-cold data
-    fn = getattr(L, f"dddm_energy_fused_{args.dtype}")
     K, W = max(1, args.steps), max(3, args.warmup)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    sets = []
-    for s in range(nsets):
-        xh, x0, t = make_inputs(1000 * rank + s, tdtype)
-        sets.append({"xh": xh.to(dev), "x0": x0.to(dev), "t": t.to(dev), "grad": torch.empty(B, M, D, dtype=tdtype, device=dev),
-                     "out": torch.zeros(4, device=dev), "wsum": torch.empty(1, device=dev),
-                     "ws": torch.zeros(L.dddm_energy_workspace_bytes(B, M), dtype=torch.uint8, device=dev)})
-    stream = torch.cuda.Stream(dev)
-    with torch.cuda.stream(stream):
-        for s in sets:  # W = mean_b w(t_b): an input of the isolated loss, computed once outside the timed region
-            _cabi.check(L.dddm_sigmoid_weight_sum_f32(s["t"].data_ptr(), W_BIAS, None, s["wsum"].data_ptr(), B,
-                                                      stream.cuda_stream))
-        if world > 1:  # global-batch weight: one float all-reduce, outside the timed region
-            for s in sets:
-                dist.all_reduce(s["wsum"])
-    stream.synchronize()
-    wscale = 1.0 / (B * world)
-
-    def launch(s, cuda_stream):
-        _cabi.check(fn(s["xh"].data_ptr(), s["x0"].data_ptr(), s["wsum"].data_ptr(), wscale, s["grad"].data_ptr(),
-                       s["out"].data_ptr(), s["ws"].data_ptr(), B, M, D, BETA, LAM, cuda_stream))
-
-    def make_runner(nstreams):
-        """Returns run_steps(n): n fused launches over the rotating sets.  With nstreams > 1 the steps
-        (independent minibatches) are issued round-robin on several streams forked/joined inside the graph."""
-        sides = [torch.cuda.Stream(dev) for _ in range(nstreams - 1)]
-
-        def capture(n):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                main = torch.cuda.current_stream()
-                for sd in sides:
-                    sd.wait_stream(main)
-                for i in range(n):
-                    st = main if i % nstreams == 0 else sides[i % nstreams - 1]
-                    launch(sets[i % nsets], st.cuda_stream)
-                for sd in sides:
-                    main.wait_stream(sd)
-            return g
-
-        if args.no_graph:
-            def run_plain(n):
-                for i in range(n):
-                    launch(sets[i % nsets], stream.cuda_stream)
-            return run_plain
-        chunk = nsets * max(1, 480 // nsets)
-        graphs = {chunk: capture(chunk)}
-
-        def run_graph(n):
-            full, rem = divmod(n, chunk)
-            for _ in range(full):
-                graphs[chunk].replay()
-            if rem:
-                if rem not in graphs:
-                    graphs[rem] = capture(rem)
-                graphs[rem].replay()
-        return run_graph
-
-    use_graph = not args.no_graph
-    nstreams = max(1, args.streams) if use_graph else 1
-    run_steps = make_runner(nstreams)
-    run_serial = make_runner(1) if nstreams > 1 else run_steps
-
+    kb = K1Bench(L, dev, args.dtype, rank, world, args.streams, args.no_graph, nsets=args.sets)
+    algo_bytes, nsets, stream = kb.algo_bytes, kb.nsets, kb.stream
     launches_before = _cabi.launch_count()
     with torch.cuda.stream(stream):
-        run_steps(W)
-        run_steps(K)  # extra untimed pass of the whole region: clocks and caches in steady state (also captures graphs)
-        run_serial(min(K, 2000))
+        kb.run_serial(W)
+        kb.run_serial(K)  # extra untimed pass of the whole region: clocks and caches in steady state (also captures graphs)
+        kb.run_multi(min(K, 2000))
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        # repeat the K-step timed region a few times and keep the median: a 5 us kernel makes a single
-        # short region noisy; every repetition times EXACTLY K steps between two events on the launch stream
-        reps = 5 if K * 5e-6 < 0.5 else 1
-        times = []
-        for _ in range(reps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            run_steps(K)
-            e1.record(stream)
-            e1.synchronize()
-            times.append(e0.elapsed_time(e1) * 1e-3)
-        # the same steps strictly serialized on ONE stream (reported for transparency, not the headline)
-        ks = min(K, 2000)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run_serial(ks)
-        e1.record(stream)
-        e1.synchronize()
-        serial_ms = e0.elapsed_time(e1) / ks
+        # HEADLINE: exactly K steps strictly serialized on ONE stream; repeated a few times (median) because a ~9 us
+        # kernel makes a single short region noisy
+        reps = 5 if K * 1e-5 < 0.5 else 1
+        elapsed, times = kb.timed(kb.run_serial, K, reps)
+        # aggregate: the same steps round-robin on several streams (labelled as such, not the headline)
+        km = min(K, 2000)
+        multi_elapsed, _ = kb.timed(kb.run_multi, km, 3)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         sampler.stop()
-    elapsed = sorted(times)[len(times) // 2]
     if world > 1:
-        tmax = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+        tmax = torch.tensor([elapsed, multi_elapsed], device=dev, dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed = float(tmax)
-    del launches_before
+        elapsed, multi_elapsed = float(tmax[0]), float(tmax[1])
+    timed_launches = _cabi.launch_count() - launches_before
     ms_per_step = 1e3 * elapsed / K
+    multi_ms = 1e3 * multi_elapsed / km
     value = world * B * K / elapsed
+    del kb.sets[:]  # free the 1 GiB of rotating sets before the other measurements
+    kernel_desc = _cabi.describe_energy(B, M, D, args.dtype)
 
-    # ---- e2e: C-ABI host-buffer session (pinned host inputs, H2D + K4 + K1 + D2H of loss & grad every step)
+    # ---- e2e: C-ABI host-buffer session (pinned host inputs in the session's packed layout: ONE H2D copy of
+    #      [xhat | x0 | t], K4 + K1, ONE D2H copy of [grad | out] per step; 4-deep pipeline)
     e2e_steps = max(3, min(args.e2e_steps, K))
-    host = []
-    for s in range(3):
-        xh, x0, t = make_inputs(5000 + 10 * rank + s, tdtype)
-        host.append((xh.contiguous().pin_memory(), x0.contiguous().pin_memory(), t.contiguous().pin_memory(),
-                     torch.empty(B, M, D, dtype=tdtype).pin_memory(), torch.zeros(4).pin_memory()))
     sess = L.dddm_session_create(B, M, D, 0 if args.dtype == "f32" else 1, local_rank)
     if not sess:
         raise SystemExit(f"dddm_session_create failed: {_cabi.strerror(L.dddm_last_error())}")
+    import ctypes
+
+    sz = [ctypes.c_size_t() for _ in range(5)]
+    _cabi.check(L.dddm_session_packed_layout(sess, *[ctypes.addressof(v) for v in sz]))
+    in_bytes, x0_off, t_off, out_bytes, out_off = [int(v.value) for v in sz]
+    host = []
+    for s in range(4):
+        xh, x0, t = make_inputs(5000 + 10 * rank + s, tdtype)
+        pin, pout = torch.zeros(in_bytes, dtype=torch.uint8).pin_memory(), torch.zeros(out_bytes, dtype=torch.uint8).pin_memory()
+        pin[:xh.numel() * esz] = xh.contiguous().view(torch.uint8).reshape(-1)
+        pin[x0_off:x0_off + x0.numel() * esz] = x0.contiguous().view(torch.uint8).reshape(-1)
+        pin[t_off:t_off + 4 * B] = t.contiguous().view(torch.uint8).reshape(-1)
+        host.append((pin, pout))
 
     def e2e_run(n):
         for i in range(n):
-            xh, x0, t, g, o = host[i % 3]
-            _cabi.check(L.dddm_session_enqueue_host(sess, xh.data_ptr(), x0.data_ptr(), t.data_ptr(), W_BIAS, BETA, LAM,
-                                                    g.data_ptr(), o.data_ptr()))
+            pin, pout = host[i % 4]
+            _cabi.check(L.dddm_session_enqueue_host(sess, pin.data_ptr(), pin.data_ptr() + x0_off, pin.data_ptr() + t_off,
+                                                    W_BIAS, BETA, LAM, pout.data_ptr(), pout.data_ptr() + out_off))
         _cabi.check(L.dddm_session_wait(sess))
 
-    e2e_run(5)
+    e2e_run(8)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -515,16 +733,20 @@ def main() -> None:
         e2e_dt = float(tmax)
     L.dddm_session_destroy(sess)
     e2e_value = world * B * e2e_steps / e2e_dt
-    h2d = (B * M * D + B * D) * esz + B * 4
-    d2h = B * M * D * esz + 16
+    h2d = t_off + 4 * B          # bytes of the one upload (payload + alignment padding of the packed layout)
+    d2h = out_off + 16           # bytes of the one download
+    if world > 1:
+        dist.barrier()
+    ceiling = copy_ceiling(dev, h2d, d2h)  # all ranks at once: the host's aggregate copy rate is the limiter at N = 8
+    if world > 1:
+        tmax = torch.tensor([ceiling["duplex_s_per_step"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ceiling["duplex_s_per_step"] = float(tmax)
+    ceiling["rows_per_s_at_ceiling"] = world * B / ceiling["duplex_s_per_step"]
+    del host
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = algo_bytes / (elapsed / K) / 1e9
-
+    multi_achieved = algo_bytes / (multi_elapsed / km) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", f"k1_traffic_{args.dtype}.json")
     if os.path.exists(tpath):  # dram bytes of ONE launch from the committed ncu --set full capture (tools/ncu_summary.py)
@@ -547,26 +769,35 @@ def main() -> None:
                    "parallelism": f"dp{world} (independent row shards, global weight pre-reduced)",
                    "l2_policy": f"{nsets} rotating input/output sets = {nsets * algo_bytes / 2**20:.0f} MiB > 8x L2 "
                                 f"(every launch reads HBM-cold inputs)",
-                   "launch": (f"CUDA graphs, programmatic dependent launch; the independent steps are issued round-robin "
-                              f"on {nstreams} streams (fork/join inside the graph) so consecutive minibatches overlap"
-                              if use_graph else "python launches, one stream"),
-                   "single_stream_ms_per_step": serial_ms,
-                   "single_stream_rows_per_s": B / (serial_ms * 1e-3),
+                   "launch": ("ONE stream, launches strictly serialized (CUDA graph of back-to-back launches, programmatic "
+                              "dependent launch): the per-launch figure a training step sees" if not args.no_graph
+                              else "python launches, one stream"),
+                   "single_stream_ms_per_step": ms_per_step,
+                   "single_stream_rows_per_s": B / (ms_per_step * 1e-3),
+                   "multi_stream": {"streams": kb.nstreams, "ms_per_step": multi_ms, "rows_per_s": world * B / (multi_ms * 1e-3),
+                                    "note": "AGGREGATE, not the headline: independent minibatches issued round-robin on "
+                                            "several streams inside one CUDA graph so that consecutive launches overlap"},
                    "timed_region": f"median of {len(times)} repetitions of exactly {K} steps (CUDA events on the "
-                                   f"launch stream)", "kernel": _cabi.describe_energy(B, M, D, args.dtype),
-                   "tuning": args.tune or "auto"},
+                                   f"launch stream)", "kernel": kernel_desc, "tuning": args.tune or "auto"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
-                     "single_stream_frac": algo_bytes / (serial_ms * 1e-3) / 1e9 / peak},
+                     "single_stream_frac": achieved / peak,
+                     "multi_stream_frac": multi_achieved / peak, "multi_stream_achieved": multi_achieved,
+                     "note": "achieved / frac are the single-launch (one stream) figures; multi_stream_* is the aggregate "
+                             "with several launches in flight; profiles/r02_k1_single_launch.md explains the gap"},
         "cpu_baseline": cpu,
         "gpu_eager_baseline": eager,
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_dt / e2e_steps,
-                "path": "dddm_session_enqueue_host (C ABI, pinned host buffers, 3-deep pipeline) + dddm_session_wait",
+                "path": "dddm_session_enqueue_host (C ABI; pinned host buffers in the session's packed layout: one "
+                        "cudaMemcpyAsync per direction and step; 4-deep pipeline) + dddm_session_wait",
+                "host_copy_ceiling": ceiling,
+                "frac_of_copy_ceiling": e2e_value / ceiling["rows_per_s_at_ceiling"],
                 "cpu_affinity": affinity},
         "gpu_launches": K,
+        "gpu_launches_counted": {"headline_region": K, "library_launches_since_warmup_start": int(timed_launches)},
         "clocks": sampler.summary(),
         "all_region_ms_per_step": [1e3 * x / K for x in times],
     }
@@ -581,16 +812,17 @@ def main() -> None:
             print(json.dumps(line), flush=True)
 
     def on_timeout() -> None:
-        emit({"error": f"auxiliary DiT/sampler measurements did not finish within {args.aux_timeout:.0f} s and were dropped"})
+        emit({"error": f"auxiliary measurements did not finish within {args.aux_timeout:.0f} s and were dropped",
+              "partial": AUX_PARTIAL})
         os._exit(0)
 
     watchdog = threading.Timer(args.aux_timeout, on_timeout)
     watchdog.daemon = True
     watchdog.start()
     try:
-        aux = run_aux(args, dev, world)
+        aux = run_aux(args, dev, world, rank, L, peak)
     except Exception as exc:  # noqa: BLE001 - report, keep the headline
-        aux = {"error": f"{type(exc).__name__}: {exc}"}
+        aux = {"error": f"{type(exc).__name__}: {exc}", "partial": AUX_PARTIAL}
     watchdog.cancel()
     emit(aux)
     if world > 1:

@@ -374,6 +374,75 @@ def _measure_throughput(args, dev, world, steps: int, warmup: int) -> dict:
             "model": "DDDMDiT(default, 14.5M params)", "optimizer": "AdamW(fused)", "n_gpus": world}
 
 
+def dp_parity(args, dev, world, batch_per_rank: int = 16) -> dict:
+    """Multi-rank parity ON HARDWARE: one step of the NCCL launcher in its production form (two CUDA graphs with the
+    eager all-reduces of sum_b w(t_b) and of the flat gradient between them) against the reference recipe run by ONE
+    process on the GLOBAL batch (``train_cifar10_dit.py:152-169``: zero_grad -> backward -> clip_grad_norm_, with the
+    loss of ``dddm/training.py:84-85``).  Every rank records the noise its step consumed (the CUDA RNG state is saved
+    before the step and the draws t, eps, xi are replayed in the step's order afterwards), rank 0 gathers all shards
+    once, recomputes loss and clipped gradient from the same weights through the single-GPU path and reports the
+    relative differences.  fp32 backbone unless ``args.precision`` says otherwise (expect <= 1e-6 in fp32)."""
+    import copy as _copy
+
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    a = _copy.copy(args)
+    a.batch, a.synthetic, a.cuda_graph = batch_per_rank, True, True
+    try:
+        tr = Trainer(a, dev, world)
+        x0 = tr.synthetic_batch()
+        tr.step(x0)  # captures the graphs (its warm-up steps are rolled back), then runs one step
+        torch.cuda.synchronize(dev)
+        w_before = tr.flat_master.clone()
+        rng = torch.cuda.get_rng_state(dev)
+        metrics = tr.step(x0)
+        torch.cuda.synchronize(dev)
+        g_dp = tr.flat_master_grad.clone()  # all-reduced (AVG) and clipped, as the optimizer saw it
+        loss_dp = metrics.tensor[:1].clone().double()
+        if world > 1:
+            dist.all_reduce(loss_dp, op=dist.ReduceOp.AVG)  # the global loss is the mean of the rank losses (equal shards)
+        # the noise this rank's step consumed, in the step's order: rand(B) (launcher), randn_like(x0), randn(B, m, ...)
+        torch.cuda.set_rng_state(rng, dev)
+        t = torch.rand(a.batch, device=dev, dtype=x0.dtype)
+        eps = torch.randn_like(x0)
+        xi = torch.randn((a.batch, a.m, *x0.shape[1:]), device=dev, dtype=x0.dtype)
+
+        def gather(v):
+            if world == 1:
+                return v
+            parts = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(parts, v.contiguous())
+            return torch.cat(parts, dim=0)
+
+        X0, T, E, XI = gather(x0), gather(t), gather(eps), gather(xi)
+        out = {"ranks": world, "batch_per_rank": a.batch, "global_batch": a.batch * world, "precision": a.precision,
+               "launcher_form": "two CUDA graphs + eager NCCL all-reduces" if tr.split_graph else "one CUDA graph (1 GPU)"}
+        if (dist.get_rank() if world > 1 else 0) == 0:
+            ref = _copy.deepcopy(tr.module)
+            flat_ref = _flatten_([p for p in ref.parameters() if p.requires_grad], torch.float32)
+            flat_ref.copy_(w_before)
+            if tr.bf16:
+                ref = ref.to(torch.bfloat16)
+            ref.train()
+            loss, _ = distributional_training_step(ref, X0, m=a.m, beta=a.beta, lam=a.lam, w_bias=a.w_bias, t=T, eps=E,
+                                                   xi=XI, global_weight=False, sync_metrics=False)
+            grads = torch.autograd.grad(loss, [p for p in ref.parameters() if p.requires_grad])
+            g_ref = torch.cat([g.reshape(-1).float() for g in grads])
+            if a.grad_clip is not None and a.grad_clip > 0:
+                g_ref = g_ref * (a.grad_clip / (torch.linalg.vector_norm(g_ref) + 1e-6)).clamp(max=1.0)
+            out.update({
+                "loss_dp": float(loss_dp), "loss_global": float(loss),
+                "loss_rel": abs(float(loss_dp) - float(loss)) / max(abs(float(loss)), 1e-30),
+                "grad_max_rel": float((g_dp - g_ref).abs().max() / g_ref.abs().max().clamp_min(1e-30)),
+                "grad_l2_rel": float(torch.linalg.vector_norm(g_dp - g_ref) / torch.linalg.vector_norm(g_ref).clamp_min(1e-30)),
+                "grad_norm_after_clip": float(torch.linalg.vector_norm(g_ref)),
+            })
+        if world > 1:
+            dist.barrier()
+        return out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
+
+
 def main(argv=None) -> None:
     parser = build_parser()
     args = parser.parse_args(argv)
