@@ -64,6 +64,11 @@ SIGNATURES = {
     "dddm_colsum_f32": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
     "dddm_colsum_bf16": (c_int, [c_void_p] * 3 + [c_size_t, c_long, c_int, c_void_p]),
     "dddm_row_sqnorm_f32": (c_int, [c_void_p, c_void_p, c_long, c_long, c_void_p]),
+    "dddm_rbf_tc_padded_cols": (c_long, [c_long]),
+    "dddm_rbf_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_long, c_void_p]),
+    "dddm_rbf_tc_scratch_bytes": (c_size_t, []),
+    "dddm_rbf_kernel_sum_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_long, c_long,
+                                       c_float, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "dddm_rbf_scratch_bytes": (c_size_t, [c_long, c_long]),
     "dddm_rbf_kernel_sum_f32": (c_int, [c_void_p, c_long, c_void_p, c_void_p, c_long, c_long, c_float, c_long, c_int,
                                         c_void_p, c_size_t, c_void_p, c_void_p]),

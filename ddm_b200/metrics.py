@@ -34,8 +34,27 @@ def _kernel_sum_offdiag(a: torch.Tensor, a2: torch.Tensor, gamma: float) -> torc
     return total
 
 
+# Below this many multiply-adds per term the library-GEMM tile path is used: the fused tensor-core kernel splits the
+# inputs into two bf16 terms (2^-17 relative per product, random sign) — invisible in a mean over millions of pairs,
+# but a handful of pairs would see it at the 1e-4 level for sigma ~ 1.
+_TC_MIN_WORK = 1 << 27
+
+
+def _rbf_mmd2_tc(xf: torch.Tensor, yf: torch.Tensor, gamma: float) -> torch.Tensor:
+    """The three terms of metrics.py:157-162 through the fused tcgen05 kernel (no Gram matrix in memory)."""
+    n, m, D = xf.shape[0], yf.shape[0], xf.shape[1]
+    x2, y2 = ops.row_sqnorm(xf), ops.row_sqnorm(yf)
+    xh, xl = ops.rbf_split_bf16(xf)
+    yh, yl = ops.rbf_split_bf16(yf)
+    kxx = ops.rbf_kernel_sum_tc(xh, xl, xh, xl, x2, x2, D, gamma, True) / (n * (n - 1))
+    kyy = ops.rbf_kernel_sum_tc(yh, yl, yh, yl, y2, y2, D, gamma, True) / (m * (m - 1))
+    kxy = ops.rbf_kernel_sum_tc(xh, xl, yh, yl, x2, y2, D, gamma, False) / (n * m)
+    return kxx + kyy - 2.0 * kxy
+
+
 @torch.no_grad()
-def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0, *, allow_tf32: Optional[bool] = None) -> torch.Tensor:
+def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0, *, allow_tf32: Optional[bool] = None,
+             method: Optional[str] = None) -> torch.Tensor:
     """Unbiased MMD^2 with an RBF kernel, sigma fixed — reference ``dddm/metrics.py:140-163``.
 
     Same signature, ``ValueError`` for fewer than two samples per set, 0-dim result in the input dtype.  The three
@@ -43,7 +62,12 @@ def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0, *, allow_tf32
     diagonal mask, sum).  CUDA-only; not differentiable (the reference only calls it on detached samples,
     ``run_example.py:101``).
 
-    ``allow_tf32`` (keyword-only extension): ``None`` keeps the process-wide ``torch.backends.cuda.matmul.allow_tf32``
+    Evaluation-sized sets (n * m * D >= 2^27, e.g. the 10 000 x 3072 of configs/cifar10_dit.yaml) take the FUSED path:
+    one persistent tcgen05 kernel per term accumulates the Gram tile in tensor memory (bf16 hi/lo split of the fp32
+    inputs, fp32 accumulation) and its epilogue reads it from there — no n x n matrix ever reaches HBM
+    (``csrc/metrics_tc.cu``).  ``method='tc'`` / ``'gemm'`` force either path.
+
+    ``allow_tf32`` (keyword-only extension, library-GEMM path): ``None`` keeps the process-wide ``torch.backends.cuda.matmul.allow_tf32``
     (PyTorch's default False = the reference's fp32 Gram); ``True`` runs the Gram tiles on the TF32 tensor cores —
     10x faster at n = 10 000, D = 3072 with the result unchanged to 6 digits there, but the Gram form's cancellation
     then carries 2^-11 instead of 2^-24 of ||x||^2, so it is opt-in.
@@ -59,12 +83,16 @@ def rbf_mmd2(x: torch.Tensor, y: torch.Tensor, sigma: float = 1.0, *, allow_tf32
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32)
         try:
-            return rbf_mmd2(x, y, sigma)
+            return rbf_mmd2(x, y, sigma, method="gemm")
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
     dtype = x.dtype
     xf, yf = x.detach().float().contiguous(), y.detach().float().contiguous()
     gamma = 1.0 / (2.0 * sigma**2)
+    if method not in (None, "tc", "gemm"):
+        raise ValueError("method must be None, 'tc' (fused tensor-core kernel) or 'gemm' (library Gram tiles + fused pass)")
+    if method == "tc" or (method is None and allow_tf32 is None and min(n, m) * max(n, m) * x.shape[1] >= _TC_MIN_WORK):
+        return _rbf_mmd2_tc(xf, yf, gamma).reshape(()).to(dtype)
     x2, y2 = ops.row_sqnorm(xf), ops.row_sqnorm(yf)
     kxx = _kernel_sum_offdiag(xf, x2, gamma) / (n * (n - 1))
     kyy = _kernel_sum_offdiag(yf, y2, gamma) / (m * (m - 1))

@@ -528,3 +528,51 @@ def rbf_kernel_sum(gram: Tensor, a2: Tensor, b2: Tensor, gamma: float, diag_shif
 @rbf_kernel_sum.register_fake
 def _(gram, a2, b2, gamma, diag_shift, skip_diag):
     return gram.new_empty(1, dtype=torch.float64)
+
+
+@torch.library.custom_op("ddm_b200::rbf_split_bf16", mutates_args=())
+def rbf_split_bf16(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """x fp32 [n, D] -> (hi, lo) bf16 [n, Dp] with x ~= hi + lo (Dp = D rounded up to 64, zero padded)."""
+    _require_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError("rbf_split_bf16 expects a 2-D float32 tensor")
+    x = x.contiguous()
+    n, D = x.shape
+    L = _cabi.lib()
+    Dp = int(L.dddm_rbf_tc_padded_cols(D))
+    hi = torch.empty(n, Dp, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(n, Dp, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _cabi.check(L.dddm_rbf_split_bf16(_ptr(x), _ptr(hi), _ptr(lo), n, D, _stream(x)))
+    return hi, lo
+
+
+@rbf_split_bf16.register_fake
+def _(x):
+    Dp = (x.shape[1] + 63) // 64 * 64
+    return x.new_empty(x.shape[0], Dp, dtype=torch.bfloat16), x.new_empty(x.shape[0], Dp, dtype=torch.bfloat16)
+
+
+@torch.library.custom_op("ddm_b200::rbf_kernel_sum_tc", mutates_args=())
+def rbf_kernel_sum_tc(a_hi: Tensor, a_lo: Tensor, b_hi: Tensor, b_lo: Tensor, a2: Tensor, b2: Tensor, D: int, gamma: float,
+                      symmetric: bool) -> Tensor:
+    """sum_{i,j} w_ij exp(-gamma (a2_i + b2_j - 2 a_i.b_j)) from the bf16 hi/lo splits, fused on the tensor cores; fp64 [1]."""
+    _require_cuda(a_hi, a_lo, b_hi, b_lo, a2, b2)
+    for t in (a_hi, a_lo, b_hi, b_lo):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or not t.is_contiguous():
+            raise TypeError("rbf_kernel_sum_tc expects contiguous 2-D bfloat16 splits (ops.rbf_split_bf16)")
+    a2, b2 = a2.float().contiguous(), b2.float().contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=a_hi.device)
+    with torch.cuda.device(a_hi.device):
+        L = _cabi.lib()
+        nbytes = L.dddm_rbf_tc_scratch_bytes()
+        scratch = torch.empty(nbytes // 8, dtype=torch.float64, device=a_hi.device)
+        _cabi.check(L.dddm_rbf_kernel_sum_tc(_ptr(a_hi), _ptr(a_lo), _ptr(b_hi), _ptr(b_lo), _ptr(a2), _ptr(b2), a_hi.shape[0],
+                                             b_hi.shape[0], int(D), float(gamma), int(bool(symmetric)), _ptr(scratch), nbytes,
+                                             _ptr(out), _stream(a_hi)))
+    return out
+
+
+@rbf_kernel_sum_tc.register_fake
+def _(a_hi, a_lo, b_hi, b_lo, a2, b2, D, gamma, symmetric):
+    return a_hi.new_empty(1, dtype=torch.float64)

@@ -227,6 +227,22 @@ int dddm_colsum_bf16(const dddm_bf16* a, dddm_bf16* out, float* scratch, size_t 
  * Partial sums are folded in double in a fixed order.  scratch: dddm_rbf_scratch_bytes(rows, cols) bytes.
  * dddm_row_sqnorm_f32: out[i] = sum_k x[i, k]^2 (metrics.py:144-145).
  * ------------------------------------------------------------------------------------------ */
+/*
+ * The same sums WITHOUT a Gram matrix in memory (the fused path rbf_mmd2 takes for evaluation-sized sets):
+ *   dddm_rbf_split_bf16     x fp32 [n, D] -> hi, lo bf16 [n, Dp], Dp = dddm_rbf_tc_padded_cols(D) (zero padded),
+ *                           x ~= hi + lo to 2^-17 relative (one streaming pre-pass per input set);
+ *   dddm_rbf_kernel_sum_tc  out[0] = sum_{i,j} w_ij exp(-gamma (a2_i + b2_j - 2 a_i.b_j)), the dot products accumulated
+ *                           in fp32 on the tensor cores as hi.hi + hi.lo + lo.hi inside a persistent tcgen05 kernel whose
+ *                           epilogue reads the accumulator from tensor memory.  symmetric != 0 (a == b, rows_a == rows_b):
+ *                           w_ij = [i != j], computed from the strict upper triangle; else w_ij = 1.
+ *                           scratch: dddm_rbf_tc_scratch_bytes() bytes.  Deterministic (static tile schedule, fixed folds).
+ */
+long dddm_rbf_tc_padded_cols(long D);
+int dddm_rbf_split_bf16(const float* x, dddm_bf16* hi, dddm_bf16* lo, long n, long D, dddm_stream_t stream);
+size_t dddm_rbf_tc_scratch_bytes(void);
+int dddm_rbf_kernel_sum_tc(const dddm_bf16* a_hi, const dddm_bf16* a_lo, const dddm_bf16* b_hi, const dddm_bf16* b_lo,
+                           const float* a2, const float* b2, long rows_a, long rows_b, long D, float gamma, int symmetric,
+                           double* scratch, size_t scratch_bytes, double* out, dddm_stream_t stream);
 int dddm_row_sqnorm_f32(const float* x, float* out, long n, long D, dddm_stream_t stream);
 size_t dddm_rbf_scratch_bytes(long rows, long cols);
 int dddm_rbf_kernel_sum_f32(const float* G, long ldg, const float* a2, const float* b2, long rows, long cols, float gamma,
