@@ -94,6 +94,11 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     // (m <= 8, any alignment) > blocked packed-fp32 kernel (m = 16, 32, aligned rows) > chunked smem-tile
     // kernel (any m <= 64)
     const int variant = tuning().variant;
+    if (variant == 6 && p.mode != kModeBwd) {  // row-pipelined cluster kernel (single-launch latency path)
+        PipePlan pp = plan_pipe(p.B, p.m, p.D, (int)sizeof(T), al, p.x0_f32 ? 2 : 1);
+        if (pp.ok) return launch_energy_pipe<T>(p, pp, stream);
+        return DDDM_ERR_UNSUPPORTED;
+    }
     if (p.x0_f32) {  // bf16 draws + fp32 x0: the TMA-staged kernel is the only one with a mixed tile
         SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 2);
         if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
@@ -329,6 +334,13 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     const bool al = ((long)D * es) % 16 == 0;
     int n;
     const int variant = tuning().variant;
+    if (variant == 6) {
+        PipePlan pp = plan_pipe(B, m, D, es, al);
+        if (pp.ok)
+            return snprintf(buf, buflen, "pipe<%s,M=%d> tma-bulk f32x2 rows-per-cluster=%d threads=%d cols=%d slab_vecs=%d window=%d smem=%zu",
+                            dtype == 1 ? "bf16" : "f32", m, pp.cluster, pp.threads, pp.cols, pp.slab_vecs, pp.window, pp.smem_bytes);
+        return snprintf(buf, buflen, "unsupported");
+    }
     if (variant == 0 || variant == 5) {
         WavePlan wp = plan_wave(B, m, D, es, al);
         if (wp.ok)

@@ -23,6 +23,15 @@ struct WavePlan {
 WavePlan plan_wave(int B, int m, int D, int elem_size, bool aligned16);
 template <typename T>
 int launch_energy_wave(const EnergyParams& p, const WavePlan& plan, cudaStream_t stream);
+// row-pipelined cluster kernel (energy_pipe.cuh): C CTAs own C rows, one column slab of each per CTA
+struct PipePlan {
+    bool ok;
+    int cluster, threads, cols, slab_vecs, window;
+    size_t smem_bytes;
+};
+PipePlan plan_pipe(int B, int m, int D, int elem_size, bool aligned16, int x0_rows = 1);
+template <typename T>
+int launch_energy_pipe(const EnergyParams& p, const PipePlan& plan, cudaStream_t stream);
 // blocked variant for m = 16, 32 (energy_blk.cuh)
 SmemPlan plan_blk(int m, int D, int elem_size, bool aligned16);
 template <typename T>

@@ -255,6 +255,74 @@ def test_wave_kernel_plans(dev):
     assert len(seen) >= 24, len(seen)
 
 
+def test_pipe_kernel_plans(dev):
+    """The row-pipelined cluster kernel (variant 6: C CTAs own C rows, one column slab of each; pass 2 of a row runs
+    while the next rows are still in flight): every cluster size, thread count, step width and request window, fp32,
+    bf16 and the mixed entry, row counts that do not fill the last cluster, slabs that do not divide D, fused and
+    split-forward modes, repeated launches on one workspace — against the fp64 oracle."""
+    from ddm_b200 import _cabi, ops
+
+    seen = set()
+    try:
+        _cabi.set_tuning("energy.variant", 6)
+        case = 0
+        for dtype, rel, name in ((torch.float32, FP32_REL, "f32"), (torch.bfloat16, BF16_REL, "bf16")):
+            for cluster in (2, 4, 8):
+                for threads, cols in ((128, 4), (256, 2), (96, 4), (64, 2)):
+                    for window in (0, 1, 3):
+                        case += 1
+                        _cabi.set_tuning("energy.cluster", cluster)
+                        _cabi.set_tuning("energy.threads", threads)
+                        _cabi.set_tuning("energy.cols", cols)
+                        _cabi.set_tuning("energy.window", window)
+                        m = 8 if case % 3 else 4
+                        B = (5, 16, 9, 1)[case % 4]
+                        D = (3072, 1000, 3072 - 40, 64)[case % 4]
+                        beta = (0.1, 1.0, 2.0)[case % 3]
+                        xh, x0 = _synthetic(B, m, D, "late" if case % 2 else "early", seed=case)
+                        xh, x0 = xh.to(dev).to(dtype), x0.to(dev).to(dtype)
+                        loss, conf, inter, grad = oracle.energy_loss(xh.double().cpu().numpy(), x0.double().cpu().numpy(),
+                                                                     beta, 1.3, 0.7)
+                        desc = _cabi.describe_energy(B, m, D, name)
+                        assert desc.startswith("pipe<"), desc
+                        seen.add(desc)
+                        for _ in range(2):
+                            out, g = _fused(xh, x0, 0.7, beta, 1.3)
+                            scale = max(abs(conf), abs(inter))
+                            assert abs(out[1] - conf) <= FP32_REL * scale and abs(out[2] - inter) <= FP32_REL * scale, desc
+                            assert abs(out[0] - loss) <= 2 * FP32_REL * 0.7 * scale, desc
+                            assert _rel(g, grad) <= rel, (desc, _rel(g, grad))
+                        o2, dist = ops.energy_terms_fwd(xh, x0, beta)  # split forward on the same kernel
+                        o2 = o2.cpu().numpy().astype(np.float64)
+                        assert abs(o2[0] - conf) <= FP32_REL * scale and abs(o2[1] - inter) <= FP32_REL * scale
+                        gc, gi = torch.tensor([0.37], device=dev), torch.tensor([-1.9], device=dev)
+                        gx, _ = ops.energy_terms_bwd(xh, x0, dist, gc, gi, beta, False)  # consumes the saved distances
+                        ref_gx, _ = oracle.energy_terms_grad(xh.double().cpu().numpy(), x0.double().cpu().numpy(), beta,
+                                                             0.37, -1.9, want_x0=True)
+                        assert np.max(np.abs(gx.float().cpu().numpy() - ref_gx)) <= rel * max(np.max(np.abs(ref_gx)), 1e-6)
+        # BASELINE config 2 at full size, default plan, fp32 + bf16 + mixed entry (bf16 draws, fp32 data)
+        for k in ("energy.cluster", "energy.threads", "energy.cols", "energy.window"):
+            _cabi.set_tuning(k, 0)
+        xh, x0 = _synthetic(128, 8, 3072, "late", seed=11)
+        for dtype, rel in ((torch.float32, FP32_REL), (torch.bfloat16, BF16_REL)):
+            a, c = xh.to(dev).to(dtype), x0.to(dev).to(dtype)
+            loss, conf, inter, grad = oracle.energy_loss(a.double().cpu().numpy(), c.double().cpu().numpy(), 0.1, 1.0, 0.5)
+            out, g = _fused(a, c, 0.5, 0.1, 1.0)
+            assert abs(out[0] - loss) <= 2e-5 * abs(conf)
+            assert _rel(g, grad) <= rel
+            out, _ = _fused(a, c, 0.5, 0.1, 1.0, want_grad=False)
+            assert abs(out[0] - loss) <= 2e-5 * abs(conf)
+        a, c = xh.to(dev).to(torch.bfloat16), x0.to(dev)
+        loss, conf, inter, grad = oracle.energy_loss(a.double().cpu().numpy(), c.double().cpu().numpy(), 0.1, 1.0, 0.5)
+        out, g = _fused(a, c, 0.5, 0.1, 1.0)
+        assert abs(out[0] - loss) <= 2e-5 * abs(conf)
+        assert _rel(g, grad) <= BF16_REL
+    finally:
+        for k in ("energy.variant", "energy.cluster", "energy.threads", "energy.cols", "energy.window"):
+            _cabi.set_tuning(k, 0)
+    assert len(seen) >= 40, len(seen)
+
+
 def test_kernel_variants_agree(dev):
     """Every launch plan (cluster size, vectors per thread, register vs smem-tile variant) is the same function."""
     from ddm_b200 import _cabi

@@ -38,7 +38,7 @@ def main():
     td = torch.float32 if a.dtype == "f32" else torch.bfloat16
     fn = getattr(L, f"dddm_energy_fused_{a.dtype}")
     desc = _cabi.describe_energy(a.B, a.m, a.D, a.dtype)
-    cluster = int(desc.split("cluster=")[1].split()[0]) if "cluster=" in desc else 1
+    cluster = int(desc.split(" cluster=")[1].split()[0]) if " cluster=" in desc else 1
     sets = []
     for s in range(a.launches):
         g = torch.Generator().manual_seed(s)
@@ -102,6 +102,11 @@ def main():
            ("pass1_done->coef_ready", 3, 4), ("  pass1_done->warp_reduce_done", 3, 8), ("  warp_reduce->after_sync1", 8, 9),
            ("  after_sync1->coef_written", 9, 10), ("  coef_written->coef_ready(sync2)", 10, 4),
            ("  warp0 vs last warp pass1 exit", 3, 11), ("coef_ready->pass2_done", 4, 5)]
+    if desc.startswith("pipe<"):  # row-pipelined cluster kernel: slots 2-4 are row 0, slots 8-10 the cluster's last row
+        seg = [("entry->inputs_ready", 0, 1), ("inputs_ready->row0_landed", 1, 2), ("row0_landed->row0_published", 2, 3),
+               ("row0_published->row0_coef", 3, 4), ("inputs_ready->last_row_landed", 1, 8),
+               ("last_row_landed->published", 8, 9), ("last_row_published->coef", 9, 10), ("last_row_coef->pass2_done", 10, 5),
+               ("inputs_ready->pass2_done", 1, 5)]
     for name, i, j in seg:
         d = (tr[2:, :, j] - tr[2:, :, i])
         print(f"  {name:<28} median {np.median(d):>7.0f} ns   p95 {np.percentile(d, 95):>7.0f} ns")
