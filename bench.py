@@ -594,11 +594,17 @@ def elementwise_rooflines(dev, peak):
           lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
                      torch.randn(n, C, H, Wd, device=dev), torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
           lambda s_: ops.bridge_step(s_[0], s_[1], s_[2], s_[3], s_[4], 1.0), 4 * n * D * 4)
-    if hasattr(ops, "bridge_step_rng"):
-        bench("K3_bridge_step_fused_noise_f32_1024",
-              lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
-                         torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
-              lambda s_: ops.bridge_step_rng(s_[0], s_[1], s_[2], s_[3], 1.0), 3 * n * D * 4)
+    # K3 with the step's two Gaussian draws fused in (z in registers, next xi written): replaces randn + randn + K3
+    bench("K3_bridge_step_fused_noise_f32_1024",
+          lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
+                     torch.empty(n, C, H, Wd, device=dev), torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
+          lambda s_: ops.bridge_step_philox_(s_[0], s_[1], s_[2], s_[3], s_[4], 1.0, seed=1234, offset_z=4096, offset_xi=8192),
+          4 * n * D * 4)
+    bench("unfused_randn_randn_K3_f32_1024",
+          lambda i: (torch.randn(n, C, H, Wd, device=dev), torch.randn(n, C, H, Wd, device=dev),
+                     torch.tensor([0.45], device=dev), torch.tensor([0.5], device=dev)),
+          lambda s_: (torch.randn_like(s_[0]), ops.bridge_step(s_[0], s_[1], torch.randn_like(s_[0]), s_[2], s_[3], 1.0)),
+          6 * n * D * 4)
     return res
 
 

@@ -75,6 +75,11 @@ SIGNATURES = {
     "dddm_sigmoid_weight_sum_f32": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "dddm_bridge_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
                                      c_void_p, c_void_p, c_long, c_long, c_void_p]),
+    "dddm_philox_increment": (c_ulonglong, [c_long]),
+    "dddm_bridge_step_philox_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                            c_ulonglong, c_ulonglong, c_ulonglong, c_long, c_long, c_void_p]),
+    "dddm_bridge_step_philox_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
+                                             c_ulonglong, c_ulonglong, c_ulonglong, c_long, c_long, c_void_p]),
     "dddm_bridge_step_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double,
                                       c_void_p, c_void_p, c_long, c_long, c_void_p]),
     "dddm_session_create": (c_void_p, [c_int, c_int, c_int, c_int, c_int]),

@@ -235,6 +235,43 @@ bridge_step_kernel(T* __restrict__ x_out, const T* __restrict__ x, const T* __re
     }
 }
 
+// Flat form for scalar (s, t) — the sampler's case: the [N, D] tensors are one array of 16-byte vectors and every
+// thread owns UNROLL of them, all loads issued before the first use (3 x UNROLL x 16 bytes in flight per thread: a
+// 50 MB update is ~10 us long, so memory-level parallelism per SM, not occupancy, decides its bandwidth).
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256)
+bridge_step_flat_kernel(T* __restrict__ x_out, const T* __restrict__ x, const T* __restrict__ xhat0,
+                        const T* __restrict__ z, const float* __restrict__ s, const float* __restrict__ t, float e2,
+                        float ome2, long nvec) {
+    const BridgeCoef c = bridge_coef(s[0], t[0], e2, ome2);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
+        float xv[UNROLL][VEC], hv[UNROLL][VEC], zv[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long v = v0 + u * stride;
+            if (v < nvec) {
+                load_pack<T, VEC>(x, v * VEC, xv[u]);
+                load_pack<T, VEC>(xhat0, v * VEC, hv[u]);
+                load_pack<T, VEC>(z, v * VEC, zv[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long v = v0 + u * stride;
+            if (v < nvec) {
+                float o[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const float mu = __fadd_rn(__fmul_rn(c.c_xt, xv[u][k]), __fmul_rn(c.c_x0, hv[u][k]));
+                    o[k] = __fadd_rn(mu, __fmul_rn(c.std, zv[u][k]));
+                }
+                store_pack<T, VEC>(x_out, v * VEC, o);
+            }
+        }
+    }
+}
+
 template <typename T>
 static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const float* s, const float* t,
                        int st_is_vector, double eps_churn, T* mu_out, float* std_out, long N, long D,
@@ -245,6 +282,17 @@ static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const f
     constexpr int V = Elem<T>::kVec;
     const bool vec = (D % V == 0) && aligned16(x) && aligned16(xhat0) && (!z || aligned16(z)) &&
                      (!x_out || aligned16(x_out)) && (!mu_out || aligned16(mu_out));
+    const float e2 = (float)(eps_churn * eps_churn), ome2 = (float)(1.0 - eps_churn * eps_churn);
+    if (vec && !st_is_vector && x_out && z && !mu_out && !std_out && x_out != x && x_out != xhat0 && x_out != z) {
+        constexpr int kUnroll = 4;
+        const long total = N * (D / V);
+        long blocks = (total + 256L * kUnroll - 1) / (256L * kUnroll);
+        const long cap = (long)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        bridge_step_flat_kernel<T, V, kUnroll><<<(unsigned)blocks, 256, 0, stream>>>(x_out, x, xhat0, z, s, t, e2, ome2, total);
+        count_launch();
+        return (int)cudaGetLastError();
+    }
     const long nvec = vec ? D / V : D;
     const int threads = nvec >= 256 ? 256 : (int)((nvec + 31) / 32 * 32);
     long tiles = (nvec + threads - 1) / threads;
@@ -252,13 +300,144 @@ static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const f
     const long max_tiles = ((long)num_sms() * 8 + rows - 1) / rows;
     if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
     dim3 grid((unsigned)tiles, (unsigned)rows);
-    const float e2 = (float)(eps_churn * eps_churn), ome2 = (float)(1.0 - eps_churn * eps_churn);
     if (vec)
         bridge_step_kernel<T, V><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
                                                                 mu_out, std_out, N, D);
     else
         bridge_step_kernel<T, 1><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
                                                                 mu_out, std_out, N, D);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---- K3 with the Gaussian draws fused in (dddm/sampling.py:27,30) ----------------------------------------------
+// The reference draws xi = randn_like(x) before the denoiser call and z = randn_like(x) before the update: two more
+// launches per step, and z costs a write and a read of N*D elements that never needs to exist.  Here z is generated
+// in registers and the NEXT step's xi is written by the same kernel.  The values are bit-identical to what
+// torch.randn_like returns for the same (seed, offset): ATen's normal kernel (distribution_elementwise_grid_stride_kernel
+// + curand_normal4) assigns element li = v + G*k + 4*G*it  (G = its total thread count, k = 0..3) component k of the
+// it-th Philox4x32-10 block of subsequence v at counter offset/4 + it, turned into normals by Box-Muller on the pairs
+// (x, y) and (z, w).  The kernel walks the same (v, it) lattice — four elements G apart per work item, each access
+// coalesced across the warp — so one Philox block serves four elements exactly as in ATen.
+struct Philox {
+    static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+    __device__ static __forceinline__ uint4 round(uint4 c, uint2 k) {
+        const uint32_t hi0 = __umulhi(kM0, c.x), lo0 = kM0 * c.x;
+        const uint32_t hi1 = __umulhi(kM1, c.z), lo1 = kM1 * c.z;
+        return make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    }
+    __device__ static __forceinline__ uint4 block(uint4 c, uint2 k) {  // Philox4x32-10
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+            c = round(c, k);
+            k.x += kW0;
+            k.y += kW1;
+        }
+        return round(c, k);
+    }
+};
+// curand's _curand_box_muller (curand_normal.h), same expression shapes so that the compiler contracts them alike
+__device__ __forceinline__ void box_muller(uint32_t x, uint32_t y, float& a, float& b) {
+    constexpr float k2Pow32Inv = 2.3283064e-10f, k2Pow32Inv2Pi = 2.3283064e-10f * 6.2831855f;
+    const float u = x * k2Pow32Inv + (k2Pow32Inv / 2);
+    const float v = y * k2Pow32Inv2Pi + (k2Pow32Inv2Pi / 2);
+    const float s = sqrtf(-2.0f * logf(u));
+    float sn, cs;
+    __sincosf(v, &sn, &cs);
+    a = sn * s;
+    b = cs * s;
+}
+__device__ __forceinline__ void normal4(unsigned long long seed, unsigned long long block_index, unsigned long long subseq,
+                                        float (&n)[4]) {
+    const uint4 c = make_uint4((uint32_t)block_index, (uint32_t)(block_index >> 32), (uint32_t)subseq, (uint32_t)(subseq >> 32));
+    const uint4 r = Philox::block(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    box_muller(r.x, r.y, n[0], n[1]);
+    box_muller(r.z, r.w, n[2], n[3]);
+}
+
+// philox = {seed, offset of the z draw, offset of the xi draw} (device memory, so that a captured graph can be
+// replayed with new offsets), or null with the three values passed by value.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bridge_step_philox_kernel(T* x_out, const T* x, const T* xhat0, T* xi_out, const float* __restrict__ s,
+                          const float* __restrict__ t, float e2, float ome2, const unsigned long long* __restrict__ philox,
+                          unsigned long long seed, unsigned long long off_z, unsigned long long off_xi, long G, int iters,
+                          long numel) {
+    if (philox != nullptr) {
+        seed = philox[0];
+        off_z = philox[1];
+        off_xi = philox[2];
+    }
+    const BridgeCoef c = bridge_coef(s[0], t[0], e2, ome2);
+    const long total = G * iters;
+    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
+        const long it = w / G, v = w - it * G;
+        const long li0 = v + 4 * G * it;
+        float xv[4], hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long li = li0 + G * k;
+            if (li < numel) {
+                xv[k] = Elem<T>::to_float(x[li]);
+                hv[k] = Elem<T>::to_float(xhat0[li]);
+            }
+        }
+        float z[4];
+        normal4(seed, off_z / 4 + (unsigned long long)it, (unsigned long long)v, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long li = li0 + G * k;
+            if (li < numel) {
+                const float mu = __fadd_rn(__fmul_rn(c.c_xt, xv[k]), __fmul_rn(c.c_x0, hv[k]));
+                const float zk = Elem<T>::to_float(Elem<T>::from_float(z[k]));  // randn_like(x) has x's dtype
+                x_out[li] = Elem<T>::from_float(__fadd_rn(mu, __fmul_rn(c.std, zk)));
+            }
+        }
+        if (xi_out != nullptr) {
+            float xi[4];
+            normal4(seed, off_xi / 4 + (unsigned long long)it, (unsigned long long)v, xi);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long li = li0 + G * k;
+                if (li < numel) xi_out[li] = Elem<T>::from_float(xi[k]);
+            }
+        }
+    }
+}
+
+// ATen's launch geometry for a normal_ over numel elements on the current device (calc_execution_policy):
+// G threads in total, `iters` Philox blocks per thread, the generator advances by 4 * iters.
+static void torch_philox_plan(long numel, long* G, long* iters) {
+    int dev = 0, max_threads = 2048;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_threads, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    const long block = 256;
+    long grid = (numel + block - 1) / block;
+    const long cap = (long)num_sms() * (max_threads / block);
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    *G = grid * block;
+    *iters = numel > 0 ? (numel - 1) / (*G * 4) + 1 : 0;
+}
+
+template <typename T>
+static int bridge_step_philox(T* x_out, const T* x, const T* xhat0, T* xi_out, const float* s, const float* t,
+                              double eps_churn, const unsigned long long* philox_dev, unsigned long long seed,
+                              unsigned long long off_z, unsigned long long off_xi, long N, long D, cudaStream_t stream) {
+    if (!x_out || !x || !xhat0 || !s || !t) return DDDM_ERR_NULL_POINTER;
+    if (N < 0 || D < 0) return DDDM_ERR_BAD_SHAPE;
+    const long numel = N * D;
+    if (numel == 0) return DDDM_OK;
+    if (!philox_dev && ((off_z | off_xi) & 3ull)) return DDDM_ERR_BAD_ARGUMENT;  // torch's offsets are multiples of 4
+    long G, iters;
+    torch_philox_plan(numel, &G, &iters);
+    const long total = G * iters;
+    long blocks = (total + 255) / 256;
+    const long cap = (long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    const float e2 = (float)(eps_churn * eps_churn), ome2 = (float)(1.0 - eps_churn * eps_churn);
+    bridge_step_philox_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(x_out, x, xhat0, xi_out, s, t, e2, ome2, philox_dev,
+                                                                        seed, off_z, off_xi, G, (int)iters, numel);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -360,6 +539,27 @@ int dddm_bridge_step_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16*
     return bridge_step<__nv_bfloat16>((__nv_bfloat16*)x_out, (const __nv_bfloat16*)x, (const __nv_bfloat16*)xhat0,
                                       (const __nv_bfloat16*)z, s, t, st_is_vector, eps_churn, (__nv_bfloat16*)mu_out,
                                       std_out, N, D, (cudaStream_t)stream);
+}
+
+unsigned long long dddm_philox_increment(long numel) {
+    long G, iters;
+    torch_philox_plan(numel, &G, &iters);
+    return 4ull * (unsigned long long)iters;
+}
+int dddm_bridge_step_philox_f32(float* x_out, const float* x, const float* xhat0, float* xi_next, const float* s,
+                                const float* t, double eps_churn, const unsigned long long* philox_dev,
+                                unsigned long long seed, unsigned long long offset_z, unsigned long long offset_xi, long N,
+                                long D, dddm_stream_t stream) {
+    return bridge_step_philox<float>(x_out, x, xhat0, xi_next, s, t, eps_churn, philox_dev, seed, offset_z, offset_xi, N, D,
+                                     (cudaStream_t)stream);
+}
+int dddm_bridge_step_philox_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16* xhat0, dddm_bf16* xi_next,
+                                 const float* s, const float* t, double eps_churn, const unsigned long long* philox_dev,
+                                 unsigned long long seed, unsigned long long offset_z, unsigned long long offset_xi, long N,
+                                 long D, dddm_stream_t stream) {
+    return bridge_step_philox<__nv_bfloat16>((__nv_bfloat16*)x_out, (const __nv_bfloat16*)x, (const __nv_bfloat16*)xhat0,
+                                             (__nv_bfloat16*)xi_next, s, t, eps_churn, philox_dev, seed, offset_z, offset_xi,
+                                             N, D, (cudaStream_t)stream);
 }
 
 int dddm_scale_inplace_f32(float* y, const float* scale, size_t n, dddm_stream_t stream) {

@@ -8,7 +8,7 @@ split energy-score gradients into autograd.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -367,6 +367,43 @@ def bridge_step(x: Tensor, xhat0: Tensor, z: Tensor, s: Tensor, t: Tensor, eps_c
 @bridge_step.register_fake
 def _(x, xhat0, z, s, t, eps_churn):
     return torch.empty_like(x)
+
+
+def philox_increment(numel: int, device) -> int:
+    """How far one ``torch.randn_like`` over ``numel`` elements advances the CUDA generator's Philox offset on
+    ``device`` (ATen's ``calc_execution_policy``)."""
+    with torch.cuda.device(device):
+        return int(_cabi.lib().dddm_philox_increment(int(numel)))
+
+
+def bridge_step_philox_(x: Tensor, xhat0: Tensor, xi_next: Optional[Tensor], s: Tensor, t: Tensor, eps_churn: float, *,
+                        philox: Optional[Tensor] = None, seed: int = 0, offset_z: int = 0, offset_xi: int = 0) -> Tensor:
+    """In-place Algorithm-2 update with the step's Gaussian draws fused in (``dddm/sampling.py:27-31``):
+    ``x <- mu(s, t, xhat0, x) + std(s, t) * z`` with ``z = randn_like(x)`` generated in registers at Philox offset
+    ``offset_z``, and — when ``xi_next`` is given — the next step's ``xi = randn_like(x)`` written at ``offset_xi``.
+    Bit-identical to drawing both with ``torch.randn_like`` at those generator offsets.  ``philox``: optional device
+    int64[3] ``{seed, offset_z, offset_xi}`` read by the kernel instead of the keyword values (CUDA-graph replay)."""
+    _require_cuda(x, xhat0, s, t)
+    if xhat0.shape != x.shape or xhat0.dtype != x.dtype:
+        raise ValueError("x and xhat0 must match in shape and dtype")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous (it is updated in place)")
+    if xi_next is not None and (xi_next.shape != x.shape or xi_next.dtype != x.dtype or not xi_next.is_contiguous()):
+        raise ValueError("xi_next must be a contiguous tensor like x")
+    if philox is not None and (philox.dtype != torch.int64 or philox.numel() < 3 or philox.device != x.device):
+        raise ValueError("philox must be a device int64 tensor {seed, offset_z, offset_xi}")
+    xhat0 = xhat0.contiguous()
+    s, t = _prep_st(s, t, x.shape[0], x.device)
+    if s.numel() != 1:
+        raise ValueError("the fused-noise update takes scalar times (one Algorithm-2 step)")
+    N = x.shape[0]
+    D = x.numel() // N if N else 0
+    mask = (1 << 64) - 1
+    with torch.cuda.device(x.device):
+        fn = getattr(_cabi.lib(), f"dddm_bridge_step_philox_{_suffix(x)}")
+        _cabi.check(fn(_ptr(x), _ptr(x), _ptr(xhat0), _ptr(xi_next), _ptr(s), _ptr(t), float(eps_churn), _ptr(philox),
+                       int(seed) & mask, int(offset_z) & mask, int(offset_xi) & mask, N, D, _stream(x)))
+    return x
 
 
 @torch.library.custom_op("ddm_b200::bridge_mu_sigma", mutates_args=())

@@ -20,6 +20,7 @@ def sample_dddm(
     *,
     noise: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
     cuda_graph: bool = False,
+    fused_noise: bool = True,
 ) -> torch.Tensor:
     """Algorithm 2 on the coarse grid t_0=0 < ... < t_N=1 — reference ``dddm/sampling.py:8-32``.
 
@@ -28,6 +29,11 @@ def sample_dddm(
     on the same device.  ``noise=(x_T, xis, zs)`` (xis/zs indexed by the loop variable k) passes the
     noise in instead.  The bridge coefficients and the update run in ONE kernel per step; the
     times stay on the device (no per-step host synchronisation).  CUDA-only.
+
+    ``fused_noise`` (default, only without ``noise``): the two Gaussian draws of a step (``sampling.py:27,30``) are
+    generated INSIDE the update kernel — z in registers, the next step's xi written by the same launch — from the
+    CUDA generator's Philox (seed, offset), bit-identical to the ``torch.randn_like`` calls they replace, and the
+    generator is left at the same offset as after the reference's loop.
 
     ``cuda_graph=True`` (only without ``noise``) captures ONE step — the two noise draws, the backbone forward and
     the K3 update — as a CUDA graph and replays it ``steps`` times with (s, t) read from device memory: at 128
@@ -49,7 +55,9 @@ def sample_dddm(
     else:
         x = noise[0].to(dev)
     if cuda_graph and noise is None and steps > 0:
-        return _sample_graphed(model, x, t_grid, steps, float(eps_churn))
+        return _sample_graphed(model, x, t_grid, steps, float(eps_churn), fused_noise)
+    if noise is None and fused_noise and steps > 0:
+        return _sample_fused_noise(model, x, t_grid, steps, float(eps_churn))
     for k in reversed(range(steps)):
         s = t_grid[k:k + 1]
         t = t_grid[k + 1:k + 2]
@@ -60,10 +68,38 @@ def sample_dddm(
     return x
 
 
+def _generator(dev: torch.device) -> torch.Generator:
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return torch.cuda.default_generators[idx]
+
+
+def _sample_fused_noise(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, eps_churn: float) -> torch.Tensor:
+    """The eager loop with both draws of a step inside K3.  Reference order per step: xi (offset o), denoiser,
+    z (o + c), next xi (o + 2c), ...: the first xi comes from torch itself, every later one from the previous
+    step's update launch at exactly the offset the reference would have drawn it."""
+    dev, B = x.device, x.shape[0]
+    gen = _generator(dev)
+    seed = gen.initial_seed()
+    c = ops.philox_increment(x.numel(), dev)
+    x = x.contiguous().clone()
+    xi = torch.randn_like(x)
+    for k in reversed(range(steps)):
+        s = t_grid[k:k + 1]
+        t = t_grid[k + 1:k + 2]
+        xhat0 = model(x, t.repeat(B), xi)
+        off = gen.get_offset()  # where the reference would draw this step's z
+        xi_next = torch.empty_like(x) if k > 0 else None
+        ops.bridge_step_philox_(x, xhat0.to(x.dtype), xi_next, s, t, eps_churn, seed=seed, offset_z=off, offset_xi=off + c)
+        gen.set_offset(off + (2 * c if k > 0 else c))
+        xi = xi_next
+    return x
+
+
 _graph_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()  # model -> {(shape, churn, device): state}
 
 
-def _sample_graphed(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, eps_churn: float) -> torch.Tensor:
+def _sample_graphed(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, eps_churn: float,
+                    fused_noise: bool = True) -> torch.Tensor:
     """Replays a cached one-step graph (captured on first use for this model / batch shape / churn: capture costs
     ~1 s, a replayed step ~1 ms).  The graph reads the model's parameters in place, so in-place weight updates are
     picked up; if parameters are re-allocated (``model.to(other_dtype)``) the key changes and a new graph is captured."""
@@ -71,14 +107,20 @@ def _sample_graphed(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, ep
     # the graph bakes in the addresses of the model's parameters and buffers: re-capture if any of them moved
     # (model.to(other dtype/device), load_state_dict(assign=True), ...)
     storage = hash(tuple(t.data_ptr() for t in list(model.parameters()) + list(model.buffers())))
-    key = (tuple(x.shape), x.dtype, float(eps_churn), str(dev), storage, model.training)
+    key = (tuple(x.shape), x.dtype, float(eps_churn), str(dev), storage, model.training, bool(fused_noise))
     per_model = _graph_cache.setdefault(model, {})
     st = per_model.get(key)
     if st is None:
         xs = x.clone()
         s_buf, t_buf = t_grid[:1].clone(), t_grid[:1].clone()
+        xi_buf = torch.zeros_like(xs) if fused_noise else None
+        ph_buf = torch.zeros(3, dtype=torch.int64, device=dev) if fused_noise else None
 
         def body():
+            if fused_noise:  # xi_buf holds this step's xi; the update draws z and overwrites xi_buf with the next xi
+                xhat0 = model(xs, t_buf.repeat(B), xi_buf)
+                ops.bridge_step_philox_(xs, xhat0.to(xs.dtype), xi_buf, s_buf, t_buf, eps_churn, philox=ph_buf)
+                return
             xi = torch.randn_like(xs)
             xhat0 = model(xs, t_buf.repeat(B), xi)
             z = torch.randn_like(xs)
@@ -94,13 +136,28 @@ def _sample_graphed(model, x: torch.Tensor, t_grid: torch.Tensor, steps: int, ep
         with torch.cuda.graph(graph):
             body()
         torch.cuda.set_rng_state(rng, dev)
-        st = per_model[key] = (graph, xs, s_buf, t_buf)
-    graph, xs, s_buf, t_buf = st
+        st = per_model[key] = (graph, xs, s_buf, t_buf, xi_buf, ph_buf)
+    graph, xs, s_buf, t_buf, xi_buf, ph_buf = st
     xs.copy_(x)
-    for k in reversed(range(steps)):
+    if fused_noise:
+        # Philox positions of every step, computed on the host once: execution step j draws z at off0 + 2c*j and
+        # the next xi at off0 + 2c*j + c (the reference's order: xi, z, xi, z, ...); the first xi is torch's own draw.
+        gen = _generator(dev)
+        seed = gen.initial_seed()
+        seed = seed - (1 << 64) if seed >= (1 << 63) else seed  # two's complement into int64
+        c = ops.philox_increment(x.numel(), dev)
+        xi_buf.copy_(torch.randn_like(xs))
+        off0 = gen.get_offset()
+        table = torch.tensor([[seed, off0 + 2 * c * j, off0 + 2 * c * j + c] for j in range(steps)],
+                             dtype=torch.int64).to(dev, non_blocking=True)
+    for j, k in enumerate(reversed(range(steps))):
         s_buf.copy_(t_grid[k:k + 1])
         t_buf.copy_(t_grid[k + 1:k + 2])
+        if fused_noise:
+            ph_buf.copy_(table[j])
         graph.replay()
+    if fused_noise:
+        gen.set_offset(off0 + 2 * c * steps - c)  # the last launch's "next xi" is not part of the stream
     return xs.clone()
 
 

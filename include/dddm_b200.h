@@ -166,6 +166,27 @@ int dddm_bridge_step_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16*
                           const float* s, const float* t, int st_is_vector, double eps_churn, dddm_bf16* mu_out,
                           float* std_out, long N, long D, dddm_stream_t stream);
 
+/*
+ * K3 with the Gaussian draws of the step fused in (dddm/sampling.py:27,30: xi = randn_like(x), z = randn_like(x)).
+ *   x_out   = c_xt*x + c_x0*xhat0 + std*z,   z generated in registers (never stored);
+ *   xi_next = the NEXT step's xi (nullable), written by the same launch.
+ * Both draws are bit-identical to torch.randn_like on the same device for the Philox (seed, offset) given:
+ * offset_z / offset_xi are the generator offsets at which the reference's two randn_like calls would run
+ * (multiples of 4; every such draw advances the generator by dddm_philox_increment(N*D)).
+ * philox_dev (nullable): device array {seed, offset_z, offset_xi} read instead of the by-value arguments, so that
+ * one captured launch can be replayed with new offsets.  s, t: one device fp32 value each.  x_out may alias x.
+ */
+unsigned long long dddm_philox_increment(long numel);
+int dddm_bridge_step_philox_f32(float* x_out, const float* x, const float* xhat0, float* xi_next, const float* s,
+                                const float* t, double eps_churn, const unsigned long long* philox_dev,
+                                unsigned long long seed, unsigned long long offset_z, unsigned long long offset_xi,
+                                long N, long D, dddm_stream_t stream);
+int dddm_bridge_step_philox_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16* xhat0, dddm_bf16* xi_next,
+                                 const float* s, const float* t, double eps_churn,
+                                 const unsigned long long* philox_dev, unsigned long long seed,
+                                 unsigned long long offset_z, unsigned long long offset_xi, long N, long D,
+                                 dddm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-buffer sessions: the same fused loss called with HOST pointers (what a reference-side
  * binding without device tensors would call; bench.py's `e2e` figure).  A session owns device

@@ -368,6 +368,69 @@ def test_fused_io_step_equals_generic_step(dev):
         ddm_b200.distributional_training_step(MixModel().to(dev), x0, m=m, beta=0.1, lam=1.0, w_bias=0.0, fused_io=True)
 
 
+def test_bridge_step_philox_matches_torch_randn(dev):
+    """K3 with the draws fused in: z (in registers) and the next xi (written out) are bit-identical to
+    torch.randn_like at the same generator (seed, offset), for sizes below / at / above ATen's grid cap, ragged
+    sizes, fp32 and bf16, offsets by value and from device memory; the update equals K3 fed with torch's z."""
+    from ddm_b200 import ops
+
+    gen = torch.cuda.default_generators[dev.index or 0]
+    for dtype in (torch.float32, torch.bfloat16):
+        for shape in ((5, 7), (64, 3, 8, 8), (128, 3072), (1024, 3, 32, 32), (1000, 1213)):
+            torch.manual_seed(2024 + len(shape))
+            x = torch.randn(shape, device=dev).to(dtype)
+            xh = torch.randn(shape, device=dev).to(dtype)
+            s, t = torch.tensor([0.35], device=dev), torch.tensor([0.4], device=dev)
+            numel = x.numel()
+            c = ops.philox_increment(numel, dev)
+            off = gen.get_offset()
+            z_ref = torch.randn_like(x)
+            assert gen.get_offset() == off + c, (shape, gen.get_offset() - off, c)  # ATen advances by what we predict
+            xi_ref = torch.randn_like(x)
+            want = ops.bridge_step(x, xh, z_ref, s, t, 0.8)
+            for via_device in (False, True):
+                xa, xi = x.clone(), torch.empty_like(x)
+                if via_device:
+                    ph = torch.tensor([gen.initial_seed(), off, off + c], dtype=torch.int64, device=dev)
+                    ops.bridge_step_philox_(xa, xh, xi, s, t, 0.8, philox=ph)
+                else:
+                    ops.bridge_step_philox_(xa, xh, xi, s, t, 0.8, seed=gen.initial_seed(), offset_z=off, offset_xi=off + c)
+                assert torch.equal(xi, xi_ref), (dtype, shape, via_device, float((xi.float() - xi_ref.float()).abs().max()))
+                assert torch.equal(xa, want), (dtype, shape, via_device, float((xa.float() - want.float()).abs().max()))
+            xb = x.clone()  # last step of a run: no next xi
+            ops.bridge_step_philox_(xb, xh, None, s, t, 0.8, seed=gen.initial_seed(), offset_z=off)
+            assert torch.equal(xb, want)
+    with pytest.raises(ValueError):
+        ops.bridge_step_philox_(x, xh, None, torch.rand(1000, device=dev), torch.rand(1000, device=dev), 0.8)
+
+
+def test_sampler_fused_noise_equals_reference_draw_order(dev):
+    """sample_dddm with the draws fused into K3 (eager and graphed) == the same run with every draw made by
+    torch.randn in the reference's order (x_T, then per step xi, z; dddm/sampling.py:23-31) and passed in;
+    the generator ends at the same offset."""
+    import ddm_b200
+
+    model = MixModel().to(dev)
+    for shape, n, steps in (((3, 8, 8), 64, 7), ((3, 32, 32), 512, 4), ((2,), 33, 5)):
+        torch.manual_seed(77)
+        xT = torch.randn((n, *shape), device=dev)
+        xis, zs = [None] * steps, [None] * steps
+        for k in reversed(range(steps)):
+            xis[k] = torch.randn_like(xT)
+            zs[k] = torch.randn_like(xT)
+        tail_ref = torch.randn(4, device=dev)
+        ref = ddm_b200.sample_dddm(model, n_samples=n, steps=steps, eps_churn=0.7, device=str(dev), data_shape=shape,
+                                   noise=(xT, xis, zs))
+        for graph in (False, True):
+            for fused in (True, False):
+                torch.manual_seed(77)
+                out = ddm_b200.sample_dddm(model, n_samples=n, steps=steps, eps_churn=0.7, device=str(dev), data_shape=shape,
+                                           cuda_graph=graph, fused_noise=fused)
+                tail = torch.randn(4, device=dev)
+                assert torch.equal(out, ref), (shape, graph, fused, float((out - ref).abs().max()))
+                assert torch.equal(tail, tail_ref), (shape, graph, fused)
+
+
 def test_sampler_cuda_graph_equals_eager(dev):
     """sample_dddm(cuda_graph=True): same Philox stream, same draws, same result as the eager loop."""
     import ddm_b200

@@ -145,10 +145,10 @@ int main() {
            (read_bytes + write_bytes) / 6452.5e3);
     printf("cudaMemcpyAsync D2D of %ld bytes (%ld moved), one stream back to back: %.2f us\n", write_bytes, 2 * write_bytes, run(0, 0, 0, 0, true, 1));
     for (int pdl = 0; pdl < 2; ++pdl)
-        for (int grid : {148, 296, 592, 1184})
+        for (int grid : {148, 296, 592, 1184, 2368, 4736})
             for (int threads : {256, 512})
                 for (int unroll : {4, 8}) {
-                    if ((long)grid * threads > 148L * 2048) continue;
+                    if (pdl == 0 && grid > 1184) continue;
                     float us = run(grid, threads, unroll, pdl, true, 0);
                     float us_r = run(grid, threads, unroll, pdl, false, 0);
                     printf("copy kernel grid=%4d threads=%4d unroll=%d pdl=%d: read+write %.2f us (%.0f GB/s, %.2f of 6452)   read-only %.2f us (%.0f GB/s)\n",
