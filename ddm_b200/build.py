@@ -21,7 +21,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "lib", "libdddm_b200.so")
 
 SOURCES = ["api.cu", "elementwise.cu", "host_session.cu", "energy_reg_f32.cu", "energy_reg_bf16.cu",
-           "energy_tile_f32.cu", "energy_tile_bf16.cu", "energy_smem_f32.cu", "energy_smem_bf16.cu", "energy_blk_f32.cu", "energy_blk_bf16.cu", "energy_wave_f32.cu", "energy_wave_bf16.cu", "energy_pipe_f32.cu", "energy_pipe_bf16.cu", "backbone_ops.cu", "metrics.cu", "metrics_tc.cu"]
+           "energy_tile_f32.cu", "energy_tile_bf16.cu", "energy_smem_f32.cu", "energy_smem_bf16.cu", "energy_blk_f32.cu", "energy_blk_bf16.cu", "energy_wave_f32.cu", "energy_wave_bf16.cu", "energy_pipe_f32.cu", "energy_pipe_bf16.cu", "energy_tc.cu", "backbone_ops.cu", "metrics.cu", "metrics_tc.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -99,6 +99,14 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
         if (pp.ok) return launch_energy_pipe<T>(p, pp, stream);
         return DDDM_ERR_UNSUPPORTED;
     }
+    if constexpr (sizeof(T) == 2) {
+        // m = 16 / 32 bf16 draws: Gram + coefficient mixing on the tensor cores (takes bf16 or fp32 x0)
+        if ((variant == 0 || variant == 7) && p.mode != kModeBwd) {
+            TcPlan tp = plan_tc(p.B, p.m, p.D, (int)sizeof(T), al);
+            if (tp.ok) return launch_energy_tc(p, tp, stream);
+            if (variant == 7) return DDDM_ERR_UNSUPPORTED;
+        }
+    }
     if (p.x0_f32) {  // bf16 draws + fp32 x0: the TMA-staged kernel is the only one with a mixed tile
         SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 2);
         if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
@@ -261,7 +269,10 @@ int dddm_energy_fused_bf16_x0f32(const dddm_bf16* xhat, const float* x0, const f
                               beta, lam, (cudaStream_t)stream, true);
 }
 int dddm_energy_fused_bf16_x0f32_supported(int m, int D) {
-    return plan_smem(m, D, 2, ((long)D * 2) % 16 == 0, 2).ok ? 1 : 0;
+    const bool al = ((long)D * 2) % 16 == 0;
+    const int variant = tuning().variant;
+    if ((variant == 0 || variant == 7) && plan_tc(1, m, D, 2, al).ok) return 1;  // tensor-core kernel, m = 16 / 32
+    return plan_smem(m, D, 2, al, 2).ok ? 1 : 0;
 }
 int dddm_energy_terms_fwd_f32(const float* xhat, const float* x0, float* dist, float* out, void* workspace, int B,
                               int m, int D, float beta, dddm_stream_t stream) {
@@ -334,6 +345,12 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     const bool al = ((long)D * es) % 16 == 0;
     int n;
     const int variant = tuning().variant;
+    if ((variant == 0 || variant == 7) && dtype == 1) {
+        TcPlan tp = plan_tc(B, m, D, es, al);
+        if (tp.ok)
+            return snprintf(buf, buflen, "tc<bf16,M=%d> tcgen05 gram + mixing, tma-2d sw128, 1 row per CTA, threads=192 smem=%zu", m, tp.smem_bytes);
+        if (variant == 7) return snprintf(buf, buflen, "unsupported");
+    }
     if (variant == 6) {
         PipePlan pp = plan_pipe(B, m, D, es, al);
         if (pp.ok)

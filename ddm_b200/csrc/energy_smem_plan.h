@@ -32,6 +32,13 @@ struct PipePlan {
 PipePlan plan_pipe(int B, int m, int D, int elem_size, bool aligned16, int x0_rows = 1);
 template <typename T>
 int launch_energy_pipe(const EnergyParams& p, const PipePlan& plan, cudaStream_t stream);
+// tensor-core kernel for m = 16, 32 bf16 draws (energy_tc.cu): Gram + coefficient mixing on tcgen05
+struct TcPlan {
+    bool ok;
+    size_t smem_bytes;
+};
+TcPlan plan_tc(int B, int m, int D, int elem_size, bool aligned16);
+int launch_energy_tc(const EnergyParams& p, const TcPlan& plan, cudaStream_t stream);
 // blocked variant for m = 16, 32 (energy_blk.cuh)
 SmemPlan plan_blk(int m, int D, int elem_size, bool aligned16);
 template <typename T>

@@ -18,7 +18,8 @@ import torch
 from ddm_b200 import _cabi
 
 
-def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, nsets_override=0, nograd=False, null=False):
+def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, nsets_override=0, nograd=False, null=False, beta=0.1,
+                regime="late"):
     tdtype = torch.float32 if dtype == "f32" else torch.bfloat16
     esz = 4 if dtype == "f32" else 2
     dev = torch.device("cuda:0")
@@ -29,7 +30,7 @@ def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, ns
     for s in range(nsets):
         g = torch.Generator().manual_seed(s)
         x0 = torch.randn(B, D, generator=g).clamp(-1, 1)
-        xh = x0[:, None] + 0.05 * torch.randn(B, m, D, generator=g)
+        xh = x0[:, None] + 0.05 * torch.randn(B, m, D, generator=g) if regime == "late" else torch.randn(B, m, D, generator=g)
         sets.append((xh.to(tdtype).to(dev), x0.to(tdtype).to(dev), torch.empty(B, m, D, dtype=tdtype, device=dev),
                      torch.zeros(4, device=dev), torch.full((1,), 0.5 * B, device=dev),
                      torch.zeros(L.dddm_energy_workspace_bytes(B, m), dtype=torch.uint8, device=dev)))
@@ -47,7 +48,7 @@ def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, ns
             _cabi.check(L.dddm_sigmoid_weight_sum_f32(tnull.data_ptr(), 0.0, None, w.data_ptr(), 32, cs))
             return
         _cabi.check(fn(xh.data_ptr(), x0.data_ptr(), w.data_ptr(), 1.0 / B, None if nograd else gr.data_ptr(),
-                       out.data_ptr(), ws.data_ptr(), B, m, D, 0.1, 1.0, cs))
+                       out.data_ptr(), ws.data_ptr(), B, m, D, float(beta), 1.0, cs))
 
     chunk = nsets * max(1, 240 // nsets)
     graph = torch.cuda.CUDAGraph()

@@ -102,6 +102,14 @@ def main():
            ("pass1_done->coef_ready", 3, 4), ("  pass1_done->warp_reduce_done", 3, 8), ("  warp_reduce->after_sync1", 8, 9),
            ("  after_sync1->coef_written", 9, 10), ("  coef_written->coef_ready(sync2)", 10, 4),
            ("  warp0 vs last warp pass1 exit", 3, 11), ("coef_ready->pass2_done", 4, 5)]
+    if desc.startswith("tc<"):  # tensor-core kernel: its own stamp layout (energy_tc.cu TC_TRACE)
+        names = ["entry", "inputs_ready", "tma_pass1_issued", "tma_pass2_issued", "gram_committed", "pass2_mmas_committed",
+                 "conf_pass_done", "gram_in_smem", "coef_ready", "epilogue_done", "row_done", "row_published"]
+        print("tensor-core kernel stamps, ns after inputs_ready (median / max over CTAs, mean over launches 2..):")
+        for k, name in enumerate(names):
+            dlt = tr[2:, :, k] - tr[2:, :, 1]
+            print(f"  {name:<24}{np.median(dlt, axis=1).mean():>10.0f}{dlt.max(axis=1).mean():>10.0f}")
+        return
     if desc.startswith("pipe<"):  # row-pipelined cluster kernel: slots 2-4 are row 0, slots 8-10 the cluster's last row
         seg = [("entry->inputs_ready", 0, 1), ("inputs_ready->row0_landed", 1, 2), ("row0_landed->row0_published", 2, 3),
                ("row0_published->row0_coef", 3, 4), ("inputs_ready->last_row_landed", 1, 8),
