@@ -31,23 +31,34 @@
 namespace dddm {
 
 namespace {
-constexpr int kTcThreads = 192;     // 6 warps
-constexpr int kTcWorkers = 128;     // warps 2..5
-constexpr int kTcStageKB = 4;       // 64-column K-blocks per pipeline stage (256 columns)
-constexpr int kTcAccBufs = 4;       // gradient accumulators in TMEM (32 columns each)
-constexpr int kTcTmemCols = 256;    // 32 (Gram) + 4 x 32 (gradient), power of two
-constexpr float kTcFlagTau = 1.0f / 256.0f;
+constexpr int kTcWorkerWarps = 8;
+constexpr int kTcWorkers = kTcWorkerWarps * 32;  // warps 2..9
+constexpr int kTcThreads = 64 + kTcWorkers;      // + TMA producer warp + MMA warp
+constexpr int kTcStageKB = 8;                    // 64-column K-blocks per pipeline stage (512 columns): few, fat stages —
+                                                 // the workers' per-stage wait / fence / arrive round trip is latency, not work
+constexpr int kTcOutTiles = 3;                   // epilogue staging tiles per group (a TMA store holds its tile ~1.5 us)
+constexpr int kTcGramAccs = 4;                   // independent Gram accumulators (32 columns each), summed at read-out, so that
+                                                 // consecutive MMAs never wait for their predecessor's accumulator
+constexpr int kTcAccBufs = 4;                    // gradient accumulators in TMEM (64 columns each: hi and lo products)
+constexpr int kTcGradCol0 = kTcGramAccs * 32;    // first TMEM column of the gradient accumulators
+constexpr int kTcTmemCols = 512;                 // 4 x 32 (Gram) + 4 x 64 (gradient) = 384 -> next power of two
+constexpr float kTcTauDist = 1.0f / 256.0f;      // z-space: below this the Gram form of d2 is replaced by direct differences
+constexpr float kTcTauGrad = 1.0f / 65536.0f;    // x-space: below this the mixing form of the gradient is replaced too
 
 template <int M>
 struct TcCfg {
     static constexpr int kSub = M * 128;               // bytes of one K-block sub-tile (M rows x 64 bf16)
     static constexpr int kStageBytes = kTcStageKB * kSub;
-    static constexpr int kStages = (M == 32) ? 6 : 8;  // 96 KB / 64 KB ring
+    static constexpr int kStages = (M == 32) ? 3 : 5;
     static constexpr int kRing = kStages * kStageBytes;
-    static constexpr int kPad = 128 * 128;             // the M = 128 Gram descriptor reads 128 rows from a sub-tile base
+    static constexpr int kOutTile = M * 256;             // one epilogue staging tile: M draws x 128 columns bf16
+    static constexpr int kOut = 2 * kTcOutTiles * kOutTile;  // two epilogue groups x kTcOutTiles; doubles as the slack the
+                                                         // M = 128 Gram descriptor reads past the last sub-tile (16 KB)
     static constexpr int kPairs = M * (M - 1) / 2;
     static constexpr int kP = M + kPairs;
-    static constexpr int kCoefBytes = M * M * 2;       // one bf16 coefficient matrix in core-matrix layout
+    static constexpr int kCoefBytes = M * M * 2;         // one bf16 coefficient matrix in core-matrix layout
+    static constexpr int kItems = kTcStageKB * M * 8 / kTcWorkers;  // 16-byte chunks per worker thread and stage
+    static_assert(kOut >= 128 * 128, "slack for the 128-row operand descriptor");
 };
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -56,6 +67,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int M>
 __device__ __forceinline__ int pair_index(int i, int j) {  // i < j, row-major upper triangle
     return i * M - i * (i + 1) / 2 + (j - i - 1);
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
+    v[0] = bf16lo(r.x); v[1] = bf16hi(r.x); v[2] = bf16lo(r.y); v[3] = bf16hi(r.y);
+    v[4] = bf16lo(r.z); v[5] = bf16hi(r.z); v[6] = bf16lo(r.w); v[7] = bf16hi(r.w);
 }
 }  // namespace
 
@@ -67,27 +82,30 @@ __device__ __forceinline__ int pair_index(int i, int j) {  // i < j, row-major u
 
 template <int M>
 __global__ void __launch_bounds__(kTcThreads, 1)
-energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p) {
+energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const EnergyParams p) {
     using namespace umma;
     using C = TcCfg<M>;
     constexpr int P2 = C::kPairs, P = C::kP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* x0s = reinterpret_cast<float*>(ring + C::kRing + C::kPad);  // [D] fp32 copy of the row's x0
+    unsigned char* outs = ring + C::kRing;                           // epilogue staging tiles [group][buffer]
+    float* x0s = reinterpret_cast<float*>(outs + C::kOut);           // [D] fp32 copy of the row's x0
 
-    __shared__ __align__(8) uint64_t full_bar[C::kStages], empty_bar[C::kStages];
+    __shared__ __align__(8) uint64_t full_bar[C::kStages], zfull_bar[C::kStages], empty_bar[C::kStages];
     __shared__ __align__(8) uint64_t acc_full[kTcAccBufs], acc_empty[kTcAccBufs];
     __shared__ __align__(8) uint64_t gram_full, gram_empty, coef_ready;
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(128) unsigned char s_chi[C::kCoefBytes], s_clo[C::kCoefBytes];
-    __shared__ float s_G[M][M + 1];
+    __shared__ __align__(128) unsigned char s_cmat[2 * C::kCoefBytes];  // [hi; lo] stacked along N: ONE MMA forms both products
+    unsigned char* s_chi = s_cmat;
+    unsigned char* s_clo = s_cmat + C::kCoefBytes;
+    __shared__ float s_G[M][M + 1];                 // Gram, then the symmetric coefficient matrix k_ij (0 where flagged)
     __shared__ float s_d2[P], s_val[P], s_coef[P];  // slot s < M: confinement of draw s; M + pair_index(i, j): pair
     __shared__ float s_c[M];                        // confinement coefficient the epilogue applies to x0
-    __shared__ float s_n0;                          // |x0|^2
-    __shared__ uint32_t s_fmask[M];                 // bit j: pair (i, j) handled by direct differences
-    __shared__ uint32_t s_cflag;                    // bit i: confinement term of draw i handled by direct differences
-    __shared__ unsigned short s_flag[P2];
-    __shared__ int s_nflag;
+    __shared__ float s_n2[M + 1];                   // |x_i|^2 (x-space scale of the gradient flags); [M] = |x0|^2
+    __shared__ uint32_t s_fmask[M];                 // bit j: gradient of pair (i, j) by direct differences
+    __shared__ uint32_t s_cflag;                    // bit i: gradient of the confinement term of draw i by direct differences
+    __shared__ unsigned short s_flag[P2];           // pairs whose d2 is recomputed by direct differences
+    __shared__ int s_nflag, s_npost;
     __shared__ unsigned char s_pi[P2], s_pj[P2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,19 +113,22 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
     const int nkb = D / 64;                                  // K-blocks per row
     const int nfill = (nkb + kTcStageKB - 1) / kTcStageKB;   // stage fills per pass
     const bool want_grad = p.grad_xhat != nullptr;
+    const int dbg = p.ld_hint;  // diagnostics (tuning "energy.ldhint"): 1 no transform, 2 no Gram MMAs, 4 no gradient MMAs, 8 no stores
 
     if (threadIdx.x == 0) {
         tma_prefetch_descriptor(&map_x);
+        tma_prefetch_descriptor(&map_g);
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1 + kTcWorkers / 32);  // the MMAs' commit + one arrival per worker warp
+            mbar_init(&zfull_bar[s], kTcWorkerWarps);
+            mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < kTcAccBufs; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kTcWorkers / 32);
+            mbar_init(&acc_empty[s], kTcWorkerWarps / 2);
         }
         mbar_init(&gram_full, 1);
-        mbar_init(&gram_empty, 1);
+        mbar_init(&gram_empty, M / 16);  // the warps that read the Gram out of tensor memory
         mbar_init(&coef_ready, 1);
         fence_barrier_init();
     }
@@ -153,26 +174,36 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc_gram = make_instr_desc(kFmtBF16, kFmtBF16, 128, M, false, false);
-            constexpr uint32_t idesc_grad = make_instr_desc(kFmtBF16, kFmtBF16, 128, M, true, false);
-            const uint32_t chi = smem_addr(s_chi), clo = smem_addr(s_clo);
+            constexpr uint32_t idesc_gram = make_instr_desc(kFmtBF16, kFmtBF16, 64, M, false, false);  // M = 64: half the operand rows
+            constexpr uint32_t idesc_grad = make_instr_desc(kFmtBF16, kFmtBF16, 128, 2 * M, true, false);
+            const uint32_t cmat = smem_addr(s_cmat);
             constexpr uint32_t kCoefLbo = 128, kCoefSbo = (M / 8) * 128;  // core matrices: next 8 k / next 8 rows
-            uint32_t n = 0, g = 0, row_it = 0;
+            uint32_t n = 0, g = 0, row_it = 0, zpar = 0;  // zpar: per-slot phase of zfull_bar (completed by Gram-pass fills only)
             for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++row_it) {
-                // ---- pass 1: Gram over D into TMEM columns [0, M) ----
+                // ---- pass 1: Gram of z = bf16(x - x0) over D into TMEM columns [0, M) ----
                 mbar_wait(&gram_empty, (row_it & 1) ^ 1);  // the previous row's Gram has been read
                 tc_fence_after_sync();
                 for (int f = 0; f < nfill; ++f, ++n) {
                     const int slot = n % C::kStages;
-                    mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
+                    mbar_wait(&zfull_bar[slot], (zpar >> slot) & 1u);  // the workers have replaced x by z in this slot
+                    zpar ^= 1u << slot;
                     tc_fence_after_sync();
-                    const uint32_t st = smem_addr(ring + (size_t)slot * C::kStageBytes);
-                    const int cnt = min(kTcStageKB, nkb - f * kTcStageKB);
-                    for (int k = 0; k < cnt; ++k) {
+                    // ONE thread issues every MMA: its instruction stream is the limit for tiles this small, so the
+                    // descriptor is built once per stage and only its start-address field (bytes >> 4) is advanced
+                    const uint64_t d0 = make_desc_kmajor_sw128(smem_addr(ring + (size_t)slot * C::kStageBytes));
+                    const int cnt = (dbg & 2) ? 0 : min(kTcStageKB, nkb - f * kTcStageKB);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {  // 16 columns = 32 bytes of K per instruction
-                            const uint64_t d = make_desc_kmajor_sw128(st + k * C::kSub + k4 * 32);
-                            mma_f16_ss(tmem_base, d, d, idesc_gram, (f | k | k4) != 0);
+                    for (int k = 0; k < kTcStageKB; ++k) {
+                        if (k < cnt) {
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {  // 16 columns = 32 bytes of K per instruction
+                                const uint64_t d = d0 + (uint64_t)((k * C::kSub + k4 * 32) >> 4);
+                                const int t = k * 4 + k4;  // k-step within the stage: rotates over the accumulators
+                                if (t < kTcGramAccs)
+                                    mma_f16_ss(tmem_base + (uint32_t)(t % kTcGramAccs) * 32u, d, d, idesc_gram, f != 0);
+                                else
+                                    mma_f16_ss(tmem_base + (uint32_t)(t % kTcGramAccs) * 32u, d, d, idesc_gram, 1);
+                            }
                         }
                     }
                     mma_commit(&empty_bar[slot]);
@@ -180,30 +211,38 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
                 mma_commit(&gram_full);
                 TC_TRACE(4);
                 if (!want_grad) continue;
-                // ---- pass 2: 128 output columns per accumulator, K = the m draws ----
+                // ---- pass 2: 128 output columns per accumulator, K = the m draws (the x tiles as they come from TMA) ----
                 mbar_wait(&coef_ready, row_it & 1);
                 tc_fence_after_sync();
+                uint64_t dcm[M / 16];  // the coefficient operand never moves
+#pragma unroll
+                for (int ks = 0; ks < M / 16; ++ks) dcm[ks] = make_desc_kmajor_core(cmat + ks * 2 * kCoefLbo, kCoefLbo, kCoefSbo);
                 for (int f = 0; f < nfill; ++f, ++n) {
                     const int slot = n % C::kStages;
                     mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t st = smem_addr(ring + (size_t)slot * C::kStageBytes);
-                    const int cnt = min(kTcStageKB, nkb - f * kTcStageKB);
-                    for (int blk = 0; blk < cnt / 2; ++blk, ++g) {
-                        const int buf = g % kTcAccBufs;
-                        mbar_wait(&acc_empty[buf], ((g / kTcAccBufs) & 1) ^ 1);
+                    const uint64_t dst0 = make_desc_mnmajor_sw128(smem_addr(ring + (size_t)slot * C::kStageBytes), C::kSub);
+                    const int nblk_stage = min(kTcStageKB, nkb - f * kTcStageKB) / 2;  // blocks of 128 output columns
+                    for (int h = 0; h < nblk_stage; h += 2) {  // two blocks at a time, their instructions alternating
+                        const int nblk = min(2, nblk_stage - h);
+                        const uint64_t da0 = dst0 + (uint64_t)((h * 2 * C::kSub) >> 4);
+                        const int buf0 = g % kTcAccBufs, buf1 = (g + 1) % kTcAccBufs;
+                        mbar_wait(&acc_empty[buf0], ((g / kTcAccBufs) & 1) ^ 1);
+                        if (nblk > 1) mbar_wait(&acc_empty[buf1], (((g + 1) / kTcAccBufs) & 1) ^ 1);
                         tc_fence_after_sync();
-                        const uint32_t acc = tmem_base + 32u + (uint32_t)buf * 32u;
-                        const uint32_t a0 = st + (uint32_t)(2 * blk) * C::kSub;
+                        const uint32_t acc0 = tmem_base + kTcGradCol0 + (uint32_t)buf0 * 64u;
+                        const uint32_t acc1 = tmem_base + kTcGradCol0 + (uint32_t)buf1 * 64u;
+                        if (!(dbg & 4)) {
 #pragma unroll
-                        for (int ks = 0; ks < M / 16; ++ks) {  // 16 draws per instruction = 2 groups of 8 tile rows
-                            const uint64_t da = make_desc_mnmajor_sw128(a0 + ks * 2048, C::kSub);
-                            const uint64_t dh = make_desc_kmajor_core(chi + ks * 2 * kCoefLbo, kCoefLbo, kCoefSbo);
-                            const uint64_t dl = make_desc_kmajor_core(clo + ks * 2 * kCoefLbo, kCoefLbo, kCoefSbo);
-                            mma_f16_ss(acc, da, dh, idesc_grad, ks != 0);
-                            mma_f16_ss(acc, da, dl, idesc_grad, 1);
+                            for (int ks = 0; ks < M / 16; ++ks) {  // 16 draws per instruction = 2 groups of 8 tile rows
+                                const uint64_t dA = da0 + (uint64_t)((ks * 2048) >> 4);
+                                const uint64_t dB = da0 + (uint64_t)((2 * C::kSub + ks * 2048) >> 4);
+                                mma_f16_ss(acc0, dA, dcm[ks], idesc_grad, ks != 0);
+                                if (nblk > 1) mma_f16_ss(acc1, dB, dcm[ks], idesc_grad, ks != 0);
+                            }
                         }
-                        mma_commit(&acc_full[buf]);
+                        mma_commit(&acc_full[buf0]);
+                        if (nblk > 1) mma_commit(&acc_full[buf1]);
+                        g += nblk;
                     }
                     mma_commit(&empty_bar[slot]);
                 }
@@ -211,93 +250,115 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
             }
         }
     } else {
-        // ===================== workers (128 threads) =====================
-        const int wt = threadIdx.x - 64;  // 0..127
-        const int ww = warp - 2;          // 0..3
+        // ===================== workers (8 warps) =====================
+        const int wt = threadIdx.x - 64;  // 0..255
+        const int ww = warp - 2;          // 0..7
         const int quarter = warp & 3;     // TMEM lanes 32 * quarter ..
-        constexpr int TPD = kTcWorkers / M;  // threads per draw in the confinement pass (4 or 8)
-        constexpr int CPT = 8 / TPD;         // 16-byte chunks of a 128-byte tile row per thread (2 or 1)
-        const int ci = wt / TPD, cpart = wt % TPD;
+        const int egroup = ww >> 2;       // epilogue: group 0 takes even 128-column blocks, group 1 odd ones
+        const bool eleader = (ww & 3) == 0 && lane == 0;  // issues the group's TMA stores
+        // transform pass: a thread owns one 16-byte chunk position (draw ti, chunk tc) of every K-block it touches
+        constexpr int ITEMS = C::kItems;                 // 4 (m = 32) or 2 (m = 16) K-blocks of a stage per thread
+        const int ti = (wt % (M * 8)) >> 3, tc = wt & 7;
+        const int tkb0 = wt / (M * 8);                   // first K-block of the stage this thread touches (0 for m = 32)
+        constexpr int KBSTEP = kTcWorkers / (M * 8);     // K-block stride between a thread's items (1 or 2)
+        const uint32_t toff = (uint32_t)ti * 128u + (uint32_t)((tc ^ (ti & 7)) << 4);
         const __nv_bfloat16* xrow0 = static_cast<const __nv_bfloat16*>(p.xhat);
-        uint32_t n = 0, g = 0, row_it = 0;
+        const bool x0f = p.x0_f32 != 0;
+        uint32_t n = 0, g = 0, row_it = 0, eblk = 0;  // eblk: blocks this epilogue group has staged (staging-buffer parity)
         for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++row_it) {
             // ---- stage x0 as fp32 (bf16 or fp32 in memory) ----
-            if (p.x0_f32) {
+            if (x0f) {
                 const float* src = static_cast<const float*>(p.x0) + (long)b * D;
                 for (int d = wt * 4; d < D; d += kTcWorkers * 4) *reinterpret_cast<float4*>(x0s + d) = *reinterpret_cast<const float4*>(src + d);
             } else {
                 const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(p.x0) + (long)b * D;
                 for (int d = wt * 8; d < D; d += kTcWorkers * 8) {
-                    const uint4 r = *reinterpret_cast<const uint4*>(src + d);
-                    *reinterpret_cast<float4*>(x0s + d) = make_float4(bf16lo(r.x), bf16hi(r.x), bf16lo(r.y), bf16hi(r.y));
-                    *reinterpret_cast<float4*>(x0s + d + 4) = make_float4(bf16lo(r.z), bf16hi(r.z), bf16lo(r.w), bf16hi(r.w));
+                    float v[8];
+                    unpack8(*reinterpret_cast<const uint4*>(src + d), v);
+                    *reinterpret_cast<float4*>(x0s + d) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(x0s + d + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
             if (wt == 0) {
                 s_nflag = 0;
+                s_npost = 0;
                 s_cflag = 0;
             }
             if (wt < M) s_fmask[wt] = 0;
+            if (wt <= M) s_n2[wt] = 0.f;
             named_bar(1, kTcWorkers);
             const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
             const float nb = (float)p.B * (float)M;
             const float pre_conf = 2.0f * W / nb;
             const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
-            // ---- pass 1 (workers): confinement distances by direct differences from the tiles the Gram consumes ----
-            float accc = 0.f, acc0 = 0.f;
+            // ---- pass 1 (workers): x -> z = bf16(x - x0) in place (same swizzled position): centred on x0 the Gram keeps
+            //      the pairwise distances without cancellation against |x|^2, and its diagonal IS the confinement term ----
+            float acc_n2 = 0.f, acc_n0 = 0.f;
             for (int f = 0; f < nfill; ++f, ++n) {
                 const int slot = n % C::kStages;
-                mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
-                const unsigned char* st = ring + (size_t)slot * C::kStageBytes;
                 const int kb0 = f * kTcStageKB, cnt = min(kTcStageKB, nkb - kb0);
-                for (int k = 0; k < cnt; ++k) {
+                mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
+                unsigned char* st = ring + (size_t)slot * C::kStageBytes;
 #pragma unroll
-                    for (int cc = 0; cc < CPT; ++cc) {
-                        const int c = cpart * CPT + cc;  // 16-byte chunk = 8 columns
-                        const uint4 r = *reinterpret_cast<const uint4*>(st + (size_t)k * C::kSub + ci * 128 + ((c ^ (ci & 7)) << 4));
-                        const float* z = x0s + (kb0 + k) * 64 + c * 8;
-                        const float4 z0 = *reinterpret_cast<const float4*>(z), z1 = *reinterpret_cast<const float4*>(z + 4);
-                        float d;
-                        d = bf16lo(r.x) - z0.x; accc = fmaf(d, d, accc);
-                        d = bf16hi(r.x) - z0.y; accc = fmaf(d, d, accc);
-                        d = bf16lo(r.y) - z0.z; accc = fmaf(d, d, accc);
-                        d = bf16hi(r.y) - z0.w; accc = fmaf(d, d, accc);
-                        d = bf16lo(r.z) - z1.x; accc = fmaf(d, d, accc);
-                        d = bf16hi(r.z) - z1.y; accc = fmaf(d, d, accc);
-                        d = bf16lo(r.w) - z1.z; accc = fmaf(d, d, accc);
-                        d = bf16hi(r.w) - z1.w; accc = fmaf(d, d, accc);
-                        if (ci == 0) {  // |x0|^2, the scale of the confinement flags
-                            acc0 = fmaf(z0.x, z0.x, acc0); acc0 = fmaf(z0.y, z0.y, acc0);
-                            acc0 = fmaf(z0.z, z0.z, acc0); acc0 = fmaf(z0.w, z0.w, acc0);
-                            acc0 = fmaf(z1.x, z1.x, acc0); acc0 = fmaf(z1.y, z1.y, acc0);
-                            acc0 = fmaf(z1.z, z1.z, acc0); acc0 = fmaf(z1.w, z1.w, acc0);
+                for (int r = 0; r < ITEMS; ++r) {
+                    const int kb = tkb0 + r * KBSTEP;
+                    if (kb < cnt && !(dbg & 1)) {
+                        const uint32_t off = (uint32_t)kb * C::kSub + toff;
+                        float x[8];
+                        unpack8(*reinterpret_cast<const uint4*>(st + off), x);
+                        const float* zp = x0s + (kb0 + kb) * 64 + tc * 8;
+                        const float4 za = *reinterpret_cast<const float4*>(zp), zb = *reinterpret_cast<const float4*>(zp + 4);
+                        const float z0[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                        uint32_t hw[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            acc_n2 = fmaf(x[e], x[e], acc_n2);
+                            acc_n2 = fmaf(x[e + 1], x[e + 1], acc_n2);
+                            hw[e >> 1] = pack_bf16x2(x[e] - z0[e], x[e + 1] - z0[e + 1]);
                         }
+                        if (ti == 0) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc_n0 = fmaf(z0[e], z0[e], acc_n0);
+                        }
+                        *reinterpret_cast<uint4*>(st + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     }
                 }
+                fence_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[slot]);
+                if (lane == 0) mbar_arrive(&zfull_bar[slot]);
             }
 #pragma unroll
-            for (int o = TPD / 2; o > 0; o >>= 1) {
-                accc += __shfl_xor_sync(0xffffffffu, accc, o);
-                acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            for (int o = 4; o > 0; o >>= 1) {  // the 8 chunk positions of a draw sit in 8 consecutive lanes
+                acc_n2 += __shfl_xor_sync(0xffffffffu, acc_n2, o);
+                acc_n0 += __shfl_xor_sync(0xffffffffu, acc_n0, o);
             }
-            if (cpart == 0) s_d2[ci] = accc;
-            if (wt == 0) s_n0 = acc0;
+            if (tc == 0) {
+                atomicAdd(&s_n2[ti], acc_n2);  // m = 16: two threads per draw (a flag scale: the order does not matter)
+                if (ti == 0) atomicAdd(&s_n2[M], acc_n0);
+            }
             if (wt == 0) TC_TRACE(6);
 
-            // ---- Gram: TMEM -> shared memory (the warp that owns TMEM lanes 0..31 = Gram rows) ----
-            if (quarter == 0) {
+            // ---- Gram: TMEM -> shared memory (a warp that owns TMEM lanes 0..31 = Gram rows) ----
+            // (an M = 64 accumulator keeps row r in lane 32 (r / 16) + r % 16: 16 rows per warp quarter)
+            if (ww >= 2 && ww < 2 + M / 16) {  // warps 4, 5: quarters 0, 1
                 mbar_wait(&gram_full, row_it & 1);
                 tc_fence_after_sync();
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base, v);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                if (lane < M) {
+                float gs[M];
 #pragma unroll
-                    for (int j = 0; j < M; ++j) s_G[lane][j] = __uint_as_float(v[j]);
+                for (int j = 0; j < M; ++j) gs[j] = 0.f;
+#pragma unroll
+                for (int a = 0; a < kTcGramAccs; ++a) {  // the partial Grams, summed in a fixed order
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * 32u, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < M; ++j) gs[j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before_sync();
+                if (lane < 16) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) s_G[quarter * 16 + lane][j] = gs[j];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&gram_empty);
@@ -305,86 +366,106 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
             named_bar(1, kTcWorkers);
             if (wt == 0) TC_TRACE(7);
 
-            // ---- distances; near-duplicates are flagged and recomputed by direct differences ----
+            // ---- distances in z-space: conf = diagonal; pairs G_ii + G_jj - 2 G_ij, near-duplicates by direct differences ----
+            if (wt < M) s_d2[wt] = fmaxf(s_G[wt][wt], 0.f);
             for (int s = wt; s < P2; s += kTcWorkers) {
                 const int i = s_pi[s], j = s_pj[s];
                 const float nn = s_G[i][i] + s_G[j][j];
                 const float d2 = nn - 2.0f * s_G[i][j];
-                if (!(d2 >= kTcFlagTau * nn)) {  // also catches NaN
+                if (!(d2 >= kTcTauDist * nn)) {  // also catches NaN
                     const int k = atomicAdd(&s_nflag, 1);
                     s_flag[k] = (unsigned short)s;
-                    atomicOr(&s_fmask[i], 1u << j);
-                    atomicOr(&s_fmask[j], 1u << i);
                 } else {
                     s_d2[M + s] = d2;
                 }
             }
-            if (wt < M) {  // confinement: exact already; flag only the gradient's mixing form
-                if (!(s_d2[wt] >= kTcFlagTau * (s_G[wt][wt] + s_n0))) atomicOr(&s_cflag, 1u << wt);
-            }
             named_bar(1, kTcWorkers);
             const int nflag = s_nflag;
-            for (int fidx = ww; fidx < nflag; fidx += kTcWorkers / 32) {
+            for (int fidx = ww; fidx < nflag; fidx += kTcWorkerWarps) {
                 const int s = s_flag[fidx];
                 const __nv_bfloat16* xi = xrow0 + ((long)b * M + s_pi[s]) * D;
                 const __nv_bfloat16* xj = xrow0 + ((long)b * M + s_pj[s]) * D;
                 float a = 0.f;
-                for (int d = lane * 8; d < D; d += 256) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(xi + d), w = *reinterpret_cast<const uint4*>(xj + d);
-                    float t;
-                    t = bf16lo(u.x) - bf16lo(w.x); a = fmaf(t, t, a);
-                    t = bf16hi(u.x) - bf16hi(w.x); a = fmaf(t, t, a);
-                    t = bf16lo(u.y) - bf16lo(w.y); a = fmaf(t, t, a);
-                    t = bf16hi(u.y) - bf16hi(w.y); a = fmaf(t, t, a);
-                    t = bf16lo(u.z) - bf16lo(w.z); a = fmaf(t, t, a);
-                    t = bf16hi(u.z) - bf16hi(w.z); a = fmaf(t, t, a);
-                    t = bf16lo(u.w) - bf16lo(w.w); a = fmaf(t, t, a);
-                    t = bf16hi(u.w) - bf16hi(w.w); a = fmaf(t, t, a);
+                for (int d0 = lane * 8; d0 < D; d0 += 1024) {  // four independent 16-byte loads per row in flight
+                    uint4 u[4], w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (d0 + q * 256 < D) {
+                            u[q] = *reinterpret_cast<const uint4*>(xi + d0 + q * 256);
+                            w[q] = *reinterpret_cast<const uint4*>(xj + d0 + q * 256);
+                        }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (d0 + q * 256 < D) {
+                            float xa[8], xb[8];
+                            unpack8(u[q], xa);
+                            unpack8(w[q], xb);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float t = xa[e] - xb[e];
+                                a = fmaf(t, t, a);
+                            }
+                        }
                 }
                 a = warp_sum(a);
                 if (lane == 0) s_d2[M + s] = a;
             }
-            if (nflag > 0) named_bar(1, kTcWorkers);
+            named_bar(1, kTcWorkers);  // also: every thread is done with the Gram values in s_G
 
-            // ---- f(d2), f'(d2) ----
+            // ---- f(d2), f'(d2); x-space flags of the gradient's mixing form; symmetric coefficient matrix into s_G ----
             for (int s = wt; s < P; s += kTcWorkers) {
                 float val, der;
-                pow_value_deriv(s_d2[s], p.pw, val, der);
+                const float d2 = s_d2[s];
+                pow_value_deriv(d2, p.pw, val, der);
                 s_val[s] = val;
-                s_coef[s] = ((s < M) ? pre_conf : pre_pair) * der;
-                if (p.dist != nullptr) p.dist[(long)b * P + s] = s_d2[s];
+                const float coef = ((s < M) ? pre_conf : pre_pair) * der;
+                s_coef[s] = coef;
+                if (p.dist != nullptr) p.dist[(long)b * P + s] = d2;
+                if (want_grad) {
+                    if (s < M) {
+                        const bool fl = !(d2 >= kTcTauGrad * (s_n2[s] + s_n2[M]));
+                        if (fl) {
+                            atomicOr(&s_cflag, 1u << s);
+                            atomicAdd(&s_npost, 1);
+                        }
+                        s_c[s] = fl ? 0.f : coef;
+                    } else {
+                        const int i = s_pi[s - M], j = s_pj[s - M];
+                        const bool fl = !(d2 >= kTcTauGrad * (s_n2[i] + s_n2[j]));
+                        if (fl) {
+                            atomicOr(&s_fmask[i], 1u << j);
+                            atomicOr(&s_fmask[j], 1u << i);
+                            atomicAdd(&s_npost, 1);
+                        }
+                        s_G[i][j] = s_G[j][i] = fl ? 0.f : coef;
+                    }
+                }
             }
             named_bar(1, kTcWorkers);
 
-            // ---- coefficient matrices C = hi + lo (bf16, K-major core-matrix layout); flagged terms left out ----
+            // ---- coefficient matrices C = hi + lo (bf16, K-major core-matrix layout): one warp per row of C ----
             if (want_grad) {
                 constexpr int kSbo = (M / 8) * 128;
-                for (int e = wt; e < M * M; e += kTcWorkers) {
-                    const int i = e / M, j = e % M;
-                    const uint32_t fm = s_fmask[i];
-                    float v;
-                    if (i == j) {
-                        v = ((s_cflag >> i) & 1u) ? 0.f : s_coef[i];
-                        for (int q = 0; q < M; ++q)
-                            if (q != i && !((fm >> q) & 1u)) v += s_coef[M + (q > i ? pair_index<M>(i, q) : pair_index<M>(q, i))];
-                    } else {
-                        v = ((fm >> j) & 1u) ? 0.f : -s_coef[M + (j > i ? pair_index<M>(i, j) : pair_index<M>(j, i))];
+                for (int i = ww; i < M; i += kTcWorkerWarps) {
+                    const float k = (lane < M && lane != i) ? s_G[i][lane] : 0.f;
+                    const float S = warp_sum(k) + s_c[i];  // c_i + sum_j k_ij over the terms the tensor core handles
+                    if (lane < M) {
+                        const float v = (lane == i) ? S : -k;
+                        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+                        const int off = (i >> 3) * kSbo + (lane >> 3) * 128 + (i & 7) * 16 + (lane & 7) * 2;
+                        *reinterpret_cast<__nv_bfloat16*>(s_chi + off) = h;
+                        *reinterpret_cast<__nv_bfloat16*>(s_clo + off) = l;
                     }
-                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-                    const int off = (i >> 3) * kSbo + (j >> 3) * 128 + (i & 7) * 16 + (j & 7) * 2;
-                    *reinterpret_cast<__nv_bfloat16*>(s_chi + off) = h;
-                    *reinterpret_cast<__nv_bfloat16*>(s_clo + off) = l;
                 }
-                if (wt < M) s_c[wt] = ((s_cflag >> wt) & 1u) ? 0.f : s_coef[wt];
-                fence_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
+                fence_async_smem();
                 named_bar(1, kTcWorkers);
                 if (wt == 0) mbar_arrive(&coef_ready);
             }
             if (wt == 0) TC_TRACE(8);
 
             // ---- row sums -> loss (one warp; the others go on) ----
-            if (ww == 3) {
+            if (ww == 7) {
                 float c = 0.f, it = 0.f;
                 for (int s = lane; s < P; s += 32) {
                     if (s < M) c += s_val[s]; else it += s_val[s];
@@ -396,63 +477,85 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
             }
 
             if (want_grad) {
-                // ---- pass 2 epilogue: accumulator (128 output columns x m draws) -> -c_i x0 -> bf16 -> HBM ----
-                __nv_bfloat16* grow = static_cast<__nv_bfloat16*>(p.grad_xhat) + (long)b * M * D;
-                for (int f = 0; f < nfill; ++f, ++n) {
-                    const int slot = n % C::kStages;
+                // ---- pass 2 epilogue: accumulator (128 output columns x m draws) -> -c_i x0 -> bf16 -> staging tile
+                //      [draw][128 columns] -> ONE TMA tensor store per block (256-byte row segments) ----
+                float cneg[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) cneg[i] = -s_c[i];
+                for (int f = 0; f < nfill; ++f) {
                     const int cnt = min(kTcStageKB, nkb - f * kTcStageKB);
                     for (int blk = 0; blk < cnt / 2; ++blk, ++g) {
+                        if ((int)(g & 1) != egroup) continue;
                         const int buf = g % kTcAccBufs;
+                        const int d0 = (f * kTcStageKB + 2 * blk) * 64;
+                        const int dl = quarter * 32 + lane;  // column within the block
+                        const float z = x0s[d0 + dl];
+                        unsigned char* ot = outs + (size_t)(egroup * kTcOutTiles + (eblk % kTcOutTiles)) * C::kOutTile;
+                        if (eleader) tma_store_wait_read<kTcOutTiles - 1>();  // the store that last read this staging tile is done with it
+                        named_bar(2 + egroup, kTcWorkers / 2);
                         mbar_wait(&acc_full[buf], (g / kTcAccBufs) & 1);
                         tc_fence_after_sync();
-                        uint32_t v[32];
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + 32u + (uint32_t)buf * 32u, v);
+                        // columns [0, M): x . C_hi, [M, 2M): x . C_lo
+                        uint32_t v[32], w[32];
+                        const uint32_t tad = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTcGradCol0 + (uint32_t)buf * 64u;
+                        tmem_ld_32x32(tad, v);
+                        if (M == 32) tmem_ld_32x32(tad + 32u, w);
                         tmem_ld_wait();
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(&acc_empty[buf]);
-                            if (blk == 0) mbar_arrive(&empty_bar[slot]);  // workers do not read the tiles in this pass
-                        }
-                        const int d = (f * kTcStageKB + 2 * blk) * 64 + quarter * 32 + lane;
-                        const float z = x0s[d];
-                        // lanes pair up: the even lane stores columns (d, d+1) of even draws, the odd lane of odd draws
-                        __nv_bfloat16* gd = grow + (d & ~1);
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
 #pragma unroll
-                        for (int i = 0; i < M; i += 2) {
-                            const float mine0 = fmaf(-s_c[i], z, __uint_as_float(v[i]));
-                            const float mine1 = fmaf(-s_c[i + 1], z, __uint_as_float(v[i + 1]));
-                            const float send = (lane & 1) ? mine0 : mine1;
-                            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
-                            const uint32_t pk = (lane & 1) ? pack_bf16x2(got, mine1) : pack_bf16x2(mine0, got);
-                            *reinterpret_cast<uint32_t*>(gd + (long)(i + (lane & 1)) * D) = pk;
+                        for (int i = 0; i < M; ++i) {
+                            const float lo = (M == 32) ? __uint_as_float(w[i]) : __uint_as_float(v[(i + 16) & 31]);
+                            const float o = fmaf(cneg[i], z, __uint_as_float(v[i]) + lo);
+                            *reinterpret_cast<__nv_bfloat16*>(ot + i * 256 + dl * 2) = __float2bfloat16_rn(o);
                         }
+                        fence_async_smem();
+                        named_bar(2 + egroup, kTcWorkers / 2);
+                        if (eleader && !(dbg & 8)) {
+                            tma_store_2d(&map_g, ot, d0, b * M);
+                            tma_store_commit();
+                        }
+                        ++eblk;
                     }
                 }
-                named_bar(1, kTcWorkers);  // every gradient row of this minibatch row has been stored by this CTA
+                n += nfill;  // the gradient pass' fills are consumed by the MMA warp alone
+                if (eleader) tma_store_wait<0>();  // this row's gradient is in memory (the post-pass below reads it back)
+                named_bar(1, kTcWorkers);
                 if (wt == 0) TC_TRACE(9);
 
                 // ---- direct-difference post-pass for the flagged terms (read-modify-write of the stored gradient) ----
-                if (s_nflag > 0 || s_cflag != 0) {
-                    for (int i = ww; i < M; i += kTcWorkers / 32) {
+                if (s_npost > 0) {
+                    __nv_bfloat16* grow = static_cast<__nv_bfloat16*>(p.grad_xhat) + (long)b * M * D;
+                    for (int i = ww; i < M; i += kTcWorkerWarps) {
                         const uint32_t fm = s_fmask[i];
                         const bool cf = (s_cflag >> i) & 1u;
                         if (fm == 0 && !cf) continue;
                         const __nv_bfloat16* xi = xrow0 + ((long)b * M + i) * D;
                         __nv_bfloat16* gi = grow + (long)i * D;
                         for (int d = lane * 8; d < D; d += 256) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(xi + d);
-                            const float xv[8] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y),
-                                                 bf16lo(u.z), bf16hi(u.z), bf16lo(u.w), bf16hi(u.w)};
-                            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            for (int j = 0; j < M; ++j) {
-                                if (!((fm >> j) & 1u)) continue;
-                                const float k = s_coef[M + (j > i ? pair_index<M>(i, j) : pair_index<M>(j, i))];
-                                const uint4 w = *reinterpret_cast<const uint4*>(xrow0 + ((long)b * M + j) * D + d);
-                                const float yv[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y),
-                                                     bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
+                            float xv[8], a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            unpack8(*reinterpret_cast<const uint4*>(xi + d), xv);
+                            uint32_t mm = fm;
+                            while (mm) {  // partners four at a time: their loads are independent
+                                int js[4];
+                                uint4 w[4];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) a[e] = fmaf(k, xv[e] - yv[e], a[e]);
+                                for (int q = 0; q < 4; ++q) {
+                                    js[q] = mm ? __ffs(mm) - 1 : -1;
+                                    if (mm) mm &= mm - 1;
+                                    if (js[q] >= 0) w[q] = *reinterpret_cast<const uint4*>(xrow0 + ((long)b * M + js[q]) * D + d);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (js[q] < 0) continue;
+                                    const int j = js[q];
+                                    const float k = s_coef[M + (j > i ? pair_index<M>(i, j) : pair_index<M>(j, i))];
+                                    float yv[8];
+                                    unpack8(w[q], yv);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) a[e] = fmaf(k, xv[e] - yv[e], a[e]);
+                                }
                             }
                             if (cf) {
                                 const float k = s_coef[i];
@@ -483,22 +586,25 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const EnergyParams p
 }
 
 // Shapes the tensor-core kernel covers: bf16 draws, m = 16 or 32, D a multiple of 128 (one accumulator = 128 output
-// columns), 16-byte aligned rows, the fp32 copy of x0 within shared memory.
+// columns), 16-byte aligned rows.
 TcPlan plan_tc(int B, int m, int D, int elem_size, bool aligned16) {
     TcPlan t{};
     t.ok = false;
     if (elem_size != 2 || !(m == 16 || m == 32) || B < 1 || D < 128 || D % 128 != 0 || !aligned16) return t;
-    const size_t ring = (m == 32) ? (size_t)TcCfg<32>::kRing + TcCfg<32>::kPad : (size_t)TcCfg<16>::kRing + TcCfg<16>::kPad;
-    t.smem_bytes = 1024 + ring + (size_t)D * 4;
-    if (t.smem_bytes > 200 * 1024) return t;  // + ~17 KB of static shared memory
+    const size_t ring = (m == 32) ? (size_t)TcCfg<32>::kRing + TcCfg<32>::kOut : (size_t)TcCfg<16>::kRing + TcCfg<16>::kOut;
+    t.smem_bytes = 1024 + ring + (size_t)D * 4;  // + the fp32 copy of the row's x0
+    if (t.smem_bytes > 232448 - 20 * 1024) return t;  // + ~18 KB of static shared memory
     t.ok = true;
     return t;
 }
 
 int launch_energy_tc(const EnergyParams& p, const TcPlan& plan, cudaStream_t stream) {
     if (p.mode == kModeBwd) return DDDM_ERR_UNSUPPORTED;
-    CUtensorMap map;
+    CUtensorMap map, map_g;
     if (umma::make_tensor_map_bf16_rows(&map, p.xhat, (uint64_t)p.B * p.m, (uint64_t)p.D, (uint32_t)p.m)) return DDDM_ERR_UNSUPPORTED;
+    // the gradient leaves through TMA tensor stores of [m draws x 128 columns] tiles (a forward-only launch never stores)
+    const void* gbase = p.grad_xhat ? p.grad_xhat : p.xhat;
+    if (umma::make_tensor_map_bf16_dense(&map_g, gbase, (uint64_t)p.B * p.m, (uint64_t)p.D, (uint32_t)p.m, 128)) return DDDM_ERR_UNSUPPORTED;
     const int sms = device_sm_count();
     const int grid = p.B < sms ? p.B : sms;
     cudaLaunchConfig_t cfg{};
@@ -515,11 +621,11 @@ int launch_energy_tc(const EnergyParams& p, const TcPlan& plan, cudaStream_t str
     if (p.m == 32) {
         static SmemOptIn configured;
         if (int r = configured.ensure(energy_tc_kernel<32>, plan.smem_bytes, 0)) return r;
-        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<32>, map, p);
+        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<32>, map, map_g, p);
     } else {
         static SmemOptIn configured;
         if (int r = configured.ensure(energy_tc_kernel<16>, plan.smem_bytes, 0)) return r;
-        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<16>, map, p);
+        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<16>, map, map_g, p);
     }
     count_launch();
     return (int)e;

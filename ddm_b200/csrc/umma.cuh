@@ -60,6 +60,19 @@ __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* map) 
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// ---- TMA: 2-D tensor store shared -> global (bulk async-group completion) ----------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int crd_inner, int crd_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_addr(src)), "r"(crd_inner), "r"(crd_outer)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's store groups may still be READING shared memory / still be in flight
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- TMEM ---------------------------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared memory).
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -159,6 +172,21 @@ inline int make_tensor_map_bf16_rows(CUtensorMap* map, const void* base, uint64_
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// row-major [rows, cols] bf16 matrix, box = [box_rows, box_cols], no swizzle (dense box in shared memory: TMA stores)
+inline int make_tensor_map_bf16_dense(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                      uint32_t box_cols) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return -1;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }

@@ -323,6 +323,72 @@ def test_pipe_kernel_plans(dev):
     assert len(seen) >= 40, len(seen)
 
 
+def _tc_inputs(B, m, D, regime, seed):
+    """late / early as _synthetic; 'mixed' = spread draws with a few near- and exact duplicates and one draw on top of
+    x0; 'dups' = identical draws (a zero-initialised output layer), one equal to x0, one a hair off."""
+    gen = torch.Generator().manual_seed(seed)
+    if regime in ("late", "early"):
+        return _synthetic(B, m, D, regime, seed)
+    x0 = torch.randn(B, D, generator=gen).clamp(-1, 1)
+    if regime == "dups":
+        xh = x0[:, None, :].repeat(1, m, 1) * 0.5
+        xh[:, 1] = x0
+        xh[:, 3] += 1e-3 * torch.randn(B, D, generator=gen)
+    else:
+        xh = x0[:, None, :] + 0.3 * torch.randn(B, m, D, generator=gen)
+        xh[:, 5] = xh[:, 2] + 2e-3 * torch.randn(B, D, generator=gen)
+        xh[:, 7] = xh[:, 2]
+        xh[:, 9] = x0 + 1e-3 * torch.randn(B, D, generator=gen)
+    return xh, x0
+
+
+@pytest.mark.parametrize("m", [16, 32])
+def test_tensor_core_kernel(dev, m):
+    """The tcgen05 kernel (variant 7; the default for m = 32 bf16 and for the mixed entry): Gram of the centred draws +
+    coefficient mixing on the tensor cores, against the fp64 oracle on the same bf16 inputs — every regime (incl. exact
+    and near duplicates, which take the direct-difference fallbacks), all betas, bf16 and fp32 x0, more rows than SMs,
+    narrow and wide rows, forward-only, saved distances of the split forward, determinism."""
+    from ddm_b200 import _cabi, ops
+
+    assert _cabi.describe_energy(128, 32, 3072, "bf16").startswith("tc<")  # the default plan at BASELINE config 3
+    try:
+        _cabi.set_tuning("energy.variant", 7)
+        case = 0
+        for B, D in ((3, 128), (8, 3072), (150, 768), (2, 12288)):
+            for regime in ("late", "early", "mixed", "dups"):
+                case += 1
+                beta = (0.1, 1.0, 2.0)[case % 3]
+                xh, x0 = _tc_inputs(B, m, D, regime, seed=case)
+                xh = xh.to(dev).to(torch.bfloat16)
+                for x0_dtype in (torch.bfloat16, torch.float32):
+                    c = x0.to(dev).to(x0_dtype)
+                    assert _cabi.describe_energy(B, m, D, "bf16").startswith("tc<")
+                    xh64, x064 = xh.double().cpu().numpy(), c.double().cpu().numpy()
+                    loss, conf, inter, grad = oracle.energy_loss(xh64, x064, beta, 1.3, 0.7)
+                    out, g = _fused(xh, c, 0.7, beta, 1.3)
+                    scale = max(abs(conf), abs(inter), 1e-30)
+                    tag = (m, B, D, regime, beta, str(x0_dtype))
+                    assert abs(out[1] - conf) <= 1e-3 * scale and abs(out[2] - inter) <= 1e-3 * scale, tag
+                    assert abs(out[0] - loss) <= 1e-3 * 0.7 * scale, tag
+                    assert _rel(g, grad) <= BF16_REL, (tag, _rel(g, grad))
+                    out2, g2 = _fused(xh, c, 0.7, beta, 1.3)  # same bits on a second launch
+                    assert np.array_equal(out, out2) and np.array_equal(g, g2), tag
+                    o3, _ = _fused(xh, c, 0.7, beta, 1.3, want_grad=False)
+                    assert np.array_equal(o3, out), tag
+                # split forward: saved squared distances (m confinement, then pairs i < j row-major)
+                c = x0.to(dev).to(torch.bfloat16)
+                o2, dist = ops.energy_terms_fwd(xh, c, beta)
+                xh64, x064 = xh.double().cpu().numpy(), c.double().cpu().numpy()
+                iu = np.triu_indices(m, 1)
+                d_ref = np.concatenate([((xh64 - x064[:, None]) ** 2).sum(-1),
+                                        ((xh64[:, :, None] - xh64[:, None]) ** 2).sum(-1)[:, iu[0], iu[1]]], axis=1)
+                d = dist.cpu().numpy().astype(np.float64)
+                ok = np.abs(d - d_ref) <= 2e-3 * d_ref + 1e-12
+                assert ok.all(), (m, B, D, regime, float(np.max(np.abs(d - d_ref) / np.maximum(d_ref, 1e-30))))
+    finally:
+        _cabi.set_tuning("energy.variant", 0)
+
+
 def test_kernel_variants_agree(dev):
     """Every launch plan (cluster size, vectors per thread, register vs smem-tile variant) is the same function."""
     from ddm_b200 import _cabi
