@@ -88,6 +88,14 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=None,
                    help="capture the whole training step in one CUDA graph (default: on with --synthetic)")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
+    p.add_argument("--grad-buckets", type=int, default=4,
+                   help="data parallel: the flat gradient is all-reduced in this many buckets, each launched from a "
+                        "backward hook on a side stream as soon as its last gradient exists (0/1 = one all-reduce after "
+                        "the backward)")
+    p.add_argument("--graph-nccl", dest="graph_nccl", action="store_true", default=None,
+                   help="several GPUs: capture the NCCL all-reduces INSIDE one whole-step CUDA graph (bucketed overlap "
+                        "included) instead of two graphs with eager collectives between them")
+    p.add_argument("--no-graph-nccl", dest="graph_nccl", action="store_false")
     return p
 
 
@@ -209,12 +217,39 @@ class Trainer:
             p.grad = self.flat_grad[off:off + n].view_as(p)          # autograd accumulates in place
             q.grad = self.flat_master_grad[off:off + n].view_as(q)   # what the optimizer reads
             off += n
+        # ---- gradient buckets: contiguous slices of the flat buffer, all-reduced from backward hooks (world > 1) ----
+        self._buckets = []          # (start, end) in elements of flat_grad
+        self._bucket_left = []      # gradients still missing per bucket in the current backward
+        self._bucket_total = []
+        self._hooks_on = False
+        self._comm_stream = None
+        nb = int(getattr(args, "grad_buckets", 4) or 0)
+        if world > 1 and nb > 1 and dev.type == "cuda":
+            total = self.flat_grad.numel()
+            bounds, owner_bucket, off, b = [0], [], 0, 0
+            for prm in grad_owner:
+                owner_bucket.append(b)
+                off += prm.numel()
+                if off >= (b + 1) * total / nb and b < nb - 1 and off < total:
+                    bounds.append(off)
+                    b += 1
+            bounds.append(total)
+            self._buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+            self._bucket_total = [owner_bucket.count(i) for i in range(len(self._buckets))]
+            self._bucket_left = list(self._bucket_total)
+            self._comm_stream = torch.cuda.Stream(dev)
+            for prm, bi in zip(grad_owner, owner_bucket):
+                prm.register_post_accumulate_grad_hook(self._make_bucket_hook(bi))
         want_graph = getattr(args, "cuda_graph", None)
         self.use_graph = dev.type == "cuda" and bool(getattr(args, "synthetic", False) if want_graph is None else want_graph)
         self.opt = torch.optim.AdamW(master, lr=args.lr, weight_decay=args.weight_decay, fused=dev.type == "cuda",
                                      capturable=self.use_graph)
-        # NCCL is never captured: with several ranks the step is split into two graphs around the collectives
-        self.split_graph = self.use_graph and (world > 1 or os.environ.get("DDDM_SPLIT_GRAPH") == "1") and loss_fn is None
+        # Several ranks: either the step is split into two graphs around eager collectives (default: robust across
+        # NCCL / driver versions), or --graph-nccl captures the collectives too (ONE graph; the bucketed all-reduces then
+        # overlap the tail of the backward inside the graph)
+        self.graph_nccl = bool(getattr(args, "graph_nccl", None) or os.environ.get("DDDM_GRAPH_NCCL") == "1") and world > 1
+        self.split_graph = (self.use_graph and (world > 1 or os.environ.get("DDDM_SPLIT_GRAPH") == "1") and loss_fn is None
+                            and not self.graph_nccl)
         self._graph = self._graph_update = None
         self._static_x0 = self._static_t = self._static_wsum = None
         self._static_metrics = None
@@ -228,10 +263,45 @@ class Trainer:
         return loss, metrics.tensor
 
     # -- the step in two device-side phases with the gradient all-reduce between them; no host synchronisation ----
-    def _fwd_bwd(self, x0: torch.Tensor, **kw) -> torch.Tensor:
+    def _make_bucket_hook(self, bi: int):
+        def hook(_param):
+            if not self._hooks_on:
+                return
+            self._bucket_left[bi] -= 1
+            if self._bucket_left[bi] == 0:
+                self._reduce_bucket(bi)
+        return hook
+
+    def _reduce_bucket(self, bi: int) -> None:
+        """All-reduce(AVG) of one bucket on the communication stream, ordered after everything the backward has queued
+        so far (all of the bucket's gradients).  Under stream capture the dependency becomes a graph edge."""
+        s, e = self._buckets[bi]
+        main = torch.cuda.current_stream(self.dev)
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+            dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+        self._bucket_left[bi] = -1  # done
+
+    def _fwd_bwd(self, x0: torch.Tensor, overlap: bool = False, **kw) -> torch.Tensor:
+        """Forward + backward.  ``overlap``: the gradient buckets are all-reduced from backward hooks on the communication
+        stream while the rest of the backward runs; on return the current stream has joined it (gradients are global)."""
         self.flat_grad.zero_()
         loss, packed = self.loss_fn(self.model, x0, **kw)
-        loss.backward()
+        if overlap and self._buckets:
+            self._bucket_left = list(self._bucket_total)
+            self._hooks_on = True
+            try:
+                loss.backward()
+            finally:
+                self._hooks_on = False
+            for bi, left in enumerate(self._bucket_left):  # parameters without a gradient this step: reduce what is left
+                if left >= 0:
+                    self._reduce_bucket(bi)
+            torch.cuda.current_stream(self.dev).wait_stream(self._comm_stream)
+        else:
+            loss.backward()
+            if overlap and self.world > 1:
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
         return packed
 
     def _update(self) -> None:
@@ -246,9 +316,7 @@ class Trainer:
             self.flat_shadow.copy_(self.flat_master)
 
     def _step_impl(self, x0: torch.Tensor) -> torch.Tensor:
-        packed = self._fwd_bwd(x0)
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        packed = self._fwd_bwd(x0, overlap=self.world > 1)
         self._update()
         return packed
 
@@ -266,9 +334,14 @@ class Trainer:
 
     def _split_step_eager(self, x0: torch.Tensor) -> torch.Tensor:
         self._weights(x0.shape[0])
-        packed = self._fwd_bwd(x0, t=self._static_t, weight_sum=self._static_wsum)
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG)
+        packed = self._fwd_bwd(x0, overlap=self.world > 1, t=self._static_t, weight_sum=self._static_wsum)
+        self._update()
+        return packed
+
+    def _whole_step_nccl(self, x0: torch.Tensor) -> torch.Tensor:
+        """--graph-nccl: the data-parallel step with both collectives in line (capturable as ONE graph)."""
+        self._weights(x0.shape[0])
+        packed = self._fwd_bwd(x0, overlap=True, t=self._static_t, weight_sum=self._static_wsum)
         self._update()
         return packed
 
@@ -294,7 +367,7 @@ class Trainer:
         self._static_x0 = x0.clone()
         self._static_t = torch.zeros(x0.shape[0], device=self.dev, dtype=x0.dtype)
         self._static_wsum = torch.zeros(1, device=self.dev)
-        eager = self._split_step_eager if self.split_graph else self._step_impl
+        eager = self._split_step_eager if self.split_graph else (self._whole_step_nccl if self.graph_nccl else self._step_impl)
         snap = self._snapshot()
         side = torch.cuda.Stream(self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -305,6 +378,11 @@ class Trainer:
         torch.cuda.synchronize(self.dev)
         self._restore(snap)
         self._graph = torch.cuda.CUDAGraph()
+        if self.graph_nccl:
+            # thread-local capture mode: the NCCL watchdog thread's event queries must not invalidate the capture
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                self._static_metrics = self._whole_step_nccl(self._static_x0)
+            return
         if not self.split_graph:
             with torch.cuda.graph(self._graph):
                 self._static_metrics = self._step_impl(self._static_x0)
@@ -415,7 +493,10 @@ def dp_parity(args, dev, world, batch_per_rank: int = 16) -> dict:
 
         X0, T, E, XI = gather(x0), gather(t), gather(eps), gather(xi)
         out = {"ranks": world, "batch_per_rank": a.batch, "global_batch": a.batch * world, "precision": a.precision,
-               "launcher_form": "two CUDA graphs + eager NCCL all-reduces" if tr.split_graph else "one CUDA graph (1 GPU)"}
+               "launcher_form": ("two CUDA graphs + eager NCCL all-reduces" if tr.split_graph else
+                                 (f"ONE CUDA graph with the NCCL all-reduces captured ({len(tr._buckets) or 1} gradient buckets "
+                                  "launched from backward hooks on a side stream)" if tr.graph_nccl else
+                                  ("one CUDA graph (1 GPU)" if tr.use_graph else "eager")))}
         if (dist.get_rank() if world > 1 else 0) == 0:
             ref = _copy.deepcopy(tr.module)
             flat_ref = _flatten_([p for p in ref.parameters() if p.requires_grad], torch.float32)

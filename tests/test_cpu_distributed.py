@@ -84,7 +84,9 @@ def test_launcher_flags_and_yaml_overlay(tmp_path):
     cfg.write_text("batch: 256\nlr: 0.001\neps_churn: 0.0\n")
     a = p.parse_args(["--config", str(cfg), "--lr", "0.5"])
     launcher.apply_yaml(p, a)
-    assert a.batch == 256 and a.lr == 0.5 and a.eps_churn == 0.0  # CLI wins over YAML, YAML over defaults
+    # CLI wins over YAML, YAML over defaults; the reference's `batch` is the GLOBAL batch (App. D.1: 256 = 4 x 64), so
+    # the YAML key lands in --global-batch and the per-GPU batch is derived from the rank count
+    assert a.global_batch == 256 and a.batch == 128 and a.lr == 0.5 and a.eps_churn == 0.0
     cfg.write_text("no_such_key: 1\n")
     a = p.parse_args(["--config", str(cfg)])
     with pytest.raises(ValueError, match="Unknown config key"):

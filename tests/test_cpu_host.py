@@ -183,7 +183,7 @@ def test_patch_reference_rebinds_imported_names():
             del sys.modules[k]
 
 
-def test_sass_shows_tma_bulk_copies_and_packed_fp32():
+def test_sass_shows_tma_bulk_copies_packed_fp32_and_tcgen05():
     """What the built library actually contains (B200_PROFILING.md, 'What proves a Blackwell-native kernel'):
     the energy kernels stage their tiles with TMA bulk copies (SASS UBLKCP, completion on mbarriers: SYNCS) and do
     their arithmetic in packed fp32 (FFMA2 / FADD2); no legacy tensor-core path (HMMA) is linked in."""
@@ -211,4 +211,14 @@ def test_sass_shows_tma_bulk_copies_and_packed_fp32():
         assert "UBLKCP" in k and "SYNCS" in k, "TMA bulk copy + mbarrier expected"
     for k in smem + blk:
         assert k.count("FFMA2") > 80 and k.count("FADD2") > 80, "packed fp32 arithmetic expected"  # bwd-only build: 112 / 86
-    assert "HMMA" not in sass and "HGMMA" not in sass
+    # tensor cores: only through tcgen05 (SASS UTCHMMA, operands by TMA tensor loads UTMALDG, accumulators read from
+    # tensor memory LDTM) — the m = 16 / 32 energy kernel and rbf_mmd2; no legacy mma.sync (HMMA.*) / wgmma (HGMMA) path
+    import re
+
+    assert not re.search(r"(?<!UTC)HMMA", sass) and "HGMMA" not in sass
+    tc = [k for k in per_kernel if "energy_tc_kernelILi32" in k.split("\n", 1)[0]]
+    mmd = [k for k in per_kernel if "rbf_gram_sum_tc_kernel" in k.split("\n", 1)[0]]
+    assert tc and mmd
+    for k in tc + mmd:
+        assert k.count("UTCHMMA") >= 8 and "UTMALDG" in k and "LDTM" in k and "UTCBAR" in k, "tcgen05 + TMA + TMEM expected"
+    assert "UTMASTG" in tc[0], "the gradient leaves through TMA tensor stores"

@@ -195,7 +195,8 @@ def test_mixed_bf16_draws_fp32_data(dev, B, m, D, regime, beta):
     if regime == "late" and D >= 1024:  # rounding x0 to bf16 (|x0| <= 1, draws 0.05 away) visibly moves the terms
         out_b, _ = _fused(xh, x0.to(torch.bfloat16), 0.7, beta, 1.3)
         assert abs(out_b[1] - conf) > 10 * abs(out[1] - conf)
-    assert _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(16, 3072) == 0
+    assert _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(16, 3072) == 1  # m = 16 / 32: the tensor-core kernel
+    assert _cabi.lib().dddm_energy_fused_bf16_x0f32_supported(24, 3072) == 0
     with pytest.raises(TypeError):
         _fused(xh.float(), x0.to(torch.bfloat16), 0.7, beta, 1.3)
 
