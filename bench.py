@@ -33,13 +33,14 @@ def workload_name(dtype: str) -> str:
     return f"isolated energy-score loss fwd+bwd, synthetic CIFAR-shaped draws B={B} m={M} D={D} {dtype} beta={BETA}"
 
 
-def make_inputs(seed: int, dtype):
+def make_inputs(seed: int, dtype, m: int = 0):
     """SURVEY.md §8(d) 'late' regime (the precision-critical one): x0 in CIFAR range, draws x0 + 0.05 noise."""
     import torch
 
+    m = m or M
     gen = torch.Generator().manual_seed(seed)
     x0 = torch.randn(B, D, generator=gen).clamp(-1, 1)
-    xh = x0[:, None, :] + 0.05 * torch.randn(B, M, D, generator=gen)
+    xh = x0[:, None, :] + 0.05 * torch.randn(B, m, D, generator=gen)
     t = torch.rand(B, generator=gen)
     return xh.to(dtype), x0.to(dtype), t
 
@@ -262,6 +263,34 @@ def run_aux(args, dev, world, rank, L, peak) -> dict:
     aux["k1_bf16_x0f32"] = k1_block("bf16", x0_f32=True)
     torch.cuda.empty_cache()
 
+    # -- BASELINE config 3 at its tensor-core point: m = 32, bf16 — the tcgen05 kernel against the blocked packed-fp32 kernel
+    def k1_m32(variant):
+        _cabi.set_tuning("energy.variant", variant)
+        try:
+            kb = K1Bench(L, dev, "bf16", rank, world, 4, args.no_graph, m=32)
+            K = 240
+            with torch.cuda.stream(kb.stream):
+                kb.run_serial(K)
+                kb.run_multi(K)
+                kb.stream.synchronize()
+                ser, _ = kb.timed(kb.run_serial, K, 3)
+                mul, _ = kb.timed(kb.run_multi, K, 3)
+            return {"kernel": _cabi.describe_energy(B, 32, D, "bf16"), "us_per_launch_1_stream": 1e6 * ser / K,
+                    "us_per_launch_4_streams": 1e6 * mul / K, "algorithmic_bytes_per_launch": kb.algo_bytes,
+                    "frac_hbm_4_streams": kb.algo_bytes / (mul / K) / 1e9 / peak}
+        finally:
+            _cabi.set_tuning("energy.variant", 0)
+
+    if world == 1:
+        tc, blk = k1_m32(7), k1_m32(4)
+        aux["k1_m32_bf16"] = {"tensor_core": tc, "blocked_fp32_pipe": blk,
+                              "speedup_1_stream": blk["us_per_launch_1_stream"] / tc["us_per_launch_1_stream"],
+                              "speedup_4_streams": blk["us_per_launch_4_streams"] / tc["us_per_launch_4_streams"],
+                              "note": "BASELINE config 3 (m=32, D=3072, bf16, beta=0.1): Gram + coefficient mixing on tcgen05 "
+                                      "(default for m = 32) vs the direct-difference kernel it replaces"}
+        torch.cuda.empty_cache()
+        aux["single_launch_copy_ceiling"] = copy_ceiling_same_bytes(dev, peak)
+
     if not args.no_elementwise and world == 1:
         aux["elementwise"] = elementwise_rooflines(dev, peak)
 
@@ -418,12 +447,14 @@ class K1Bench:
     (the headline: what a training step sees, one loss launch between the backbone's forward and backward) and with
     the independent steps issued round-robin on several streams (aggregate: consecutive minibatches overlap)."""
 
-    def __init__(self, L, dev, dtype_name, rank, world, nstreams, no_graph, nsets=0, x0_f32=False):
+    def __init__(self, L, dev, dtype_name, rank, world, nstreams, no_graph, nsets=0, x0_f32=False, m=0):
         import torch
         import torch.distributed as dist
 
         from ddm_b200 import _cabi
 
+        M = m or globals()["M"]  # BASELINE config 3 runs the same harness at m = 32
+        self.m = M
         self.torch, self.L, self.dev, self.world = torch, L, dev, world
         self.dtype_name = dtype_name
         tdtype = torch.float32 if dtype_name == "f32" else torch.bfloat16
@@ -433,9 +464,9 @@ class K1Bench:
         fn = getattr(L, f"dddm_energy_fused_{dtype_name}" + ("_x0f32" if x0_f32 else ""))
         self.sets = []
         for s in range(self.nsets):
-            xh, x0, t = make_inputs(1000 * rank + s, tdtype)
+            xh, x0, t = make_inputs(1000 * rank + s, tdtype, M)
             if x0_f32:
-                x0 = make_inputs(1000 * rank + s, torch.float32)[1]
+                x0 = make_inputs(1000 * rank + s, torch.float32, M)[1]
             self.sets.append({"xh": xh.to(dev), "x0": x0.to(dev), "t": t.to(dev),
                               "grad": torch.empty(B, M, D, dtype=tdtype, device=dev), "out": torch.zeros(4, device=dev),
                               "wsum": torch.empty(1, device=dev),
@@ -540,6 +571,44 @@ def copy_ceiling(dev, h2d_bytes, d2h_bytes, reps=20):
             "duplex_s_per_step": t_both, "bytes": [h2d_bytes, d2h_bytes],
             "how": f"{reps} back-to-back cudaMemcpyAsync of one step's bytes per direction from/to pinned host memory, "
                    "two streams, wall clock around a device synchronize"}
+
+
+def copy_ceiling_same_bytes(dev, peak):
+    """What ONE dependent launch can reach at K1's size: the driver's own device-to-device copy of the gradient's bytes
+    (12.6 MB read + 12.6 MB written), back to back on one stream over rotating HBM-cold buffers — no arithmetic, no
+    row-wise dependency.  The kernel's single-stream figure is to be read against this, not against the burst peak."""
+    import torch
+
+    nbytes = B * M * D * 4
+    nsets = max(4, -(-8 * L2_BYTES // (2 * nbytes)))
+    src = [torch.empty(nbytes, dtype=torch.uint8, device=dev).fill_(i & 255) for i in range(nsets)]
+    dst = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(nsets)]
+    stream = torch.cuda.Stream(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        for i in range(3):
+            dst[i].copy_(src[i])
+    stream.synchronize()
+    with torch.cuda.graph(g, stream=stream):
+        for i in range(nsets):
+            dst[i].copy_(src[i])
+    ts = []
+    with torch.cuda.stream(stream):
+        g.replay()
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                g.replay()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3 / (5 * nsets))
+    sec = sorted(ts)[2]
+    k1_bytes = (2 * B * M * D + B * D) * 4
+    return {"what": "cudaMemcpyAsync device-to-device of B*m*D*4 bytes, one stream, back to back, rotating sets",
+            "bytes_moved": 2 * nbytes, "us_per_copy": sec * 1e6, "GBps": 2 * nbytes / sec / 1e9,
+            "frac_of_peak": 2 * nbytes / sec / 1e9 / peak,
+            "k1_bytes_at_this_rate_us": k1_bytes / (2 * nbytes / sec) * 1e6}
 
 
 def elementwise_rooflines(dev, peak):

@@ -6,6 +6,24 @@
 #include "energy.cuh"
 #include "energy_smem_plan.h"
 
+#include <nvtx3/nvToolsExt.h>
+
+#include <cstdlib>
+
+namespace dddm {
+bool nvtx_enabled() {
+    int v = tuning().nvtx;
+    if (v < 0) {
+        const char* e = getenv("DDDM_NVTX");
+        v = (e != nullptr && e[0] == '1') ? 1 : 0;
+        tuning().nvtx = v;
+    }
+    return v != 0;
+}
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
+}  // namespace dddm
+
 namespace dddm {
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -255,18 +273,21 @@ size_t dddm_energy_dist_per_row(int m) { return m < 2 ? 0 : (size_t)m + (size_t)
 int dddm_energy_fused_f32(const float* xhat, const float* x0, const float* weight_dev, float weight_scale,
                           float* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta, float lam,
                           dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1 energy_fused f32");
     return energy_fused<float>(xhat, x0, weight_dev, weight_scale, grad_xhat, out, workspace, B, m, D, beta, lam,
                                (cudaStream_t)stream);
 }
 int dddm_energy_fused_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* weight_dev, float weight_scale,
                            dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
                            float lam, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1 energy_fused bf16");
     return energy_fused<bf16>((const bf16*)xhat, (const bf16*)x0, weight_dev, weight_scale, (bf16*)grad_xhat, out,
                               workspace, B, m, D, beta, lam, (cudaStream_t)stream);
 }
 int dddm_energy_fused_bf16_x0f32(const dddm_bf16* xhat, const float* x0, const float* weight_dev, float weight_scale,
                                  dddm_bf16* grad_xhat, float* out, void* workspace, int B, int m, int D, float beta,
                                  float lam, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1 energy_fused bf16 x0=f32");
     return energy_fused<bf16>((const bf16*)xhat, x0, weight_dev, weight_scale, (bf16*)grad_xhat, out, workspace, B, m, D,
                               beta, lam, (cudaStream_t)stream, true);
 }
@@ -278,22 +299,26 @@ int dddm_energy_fused_bf16_x0f32_supported(int m, int D) {
 }
 int dddm_energy_terms_fwd_f32(const float* xhat, const float* x0, float* dist, float* out, void* workspace, int B,
                               int m, int D, float beta, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1b energy_terms_fwd f32");
     return energy_terms_fwd<float>(xhat, x0, dist, out, workspace, B, m, D, beta, (cudaStream_t)stream);
 }
 int dddm_energy_terms_fwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, float* dist, float* out, void* workspace,
                                int B, int m, int D, float beta, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1b energy_terms_fwd bf16");
     return energy_terms_fwd<bf16>((const bf16*)xhat, (const bf16*)x0, dist, out, workspace, B, m, D, beta,
                                   (cudaStream_t)stream);
 }
 int dddm_energy_terms_bwd_f32(const float* xhat, const float* x0, const float* dist, const float* g_conf,
                               const float* g_inter, float* grad_xhat, float* grad_x0, int B, int m, int D, float beta,
                               dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1b energy_terms_bwd f32");
     return energy_terms_bwd<float>(xhat, x0, dist, g_conf, g_inter, grad_xhat, grad_x0, B, m, D, beta,
                                    (cudaStream_t)stream);
 }
 int dddm_energy_terms_bwd_bf16(const dddm_bf16* xhat, const dddm_bf16* x0, const float* dist, const float* g_conf,
                                const float* g_inter, dddm_bf16* grad_xhat, dddm_bf16* grad_x0, int B, int m, int D,
                                float beta, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K1b energy_terms_bwd bf16");
     return energy_terms_bwd<bf16>((const bf16*)xhat, (const bf16*)x0, dist, g_conf, g_inter, (bf16*)grad_xhat,
                                   (bf16*)grad_x0, B, m, D, beta, (cudaStream_t)stream);
 }
@@ -314,6 +339,7 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.ldhint")) t.ldhint = value;
     else if (!strcmp(key, "energy.sthint")) t.sthint = value;
     else if (!strcmp(key, "energy.nostore")) t.nostore = value;
+    else if (!strcmp(key, "nvtx")) t.nvtx = value ? 1 : 0;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
 }
@@ -333,6 +359,7 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.ldhint")) return t.ldhint;
     if (!strcmp(key, "energy.sthint")) return t.sthint;
     if (!strcmp(key, "energy.nostore")) return t.nostore;
+    if (!strcmp(key, "nvtx")) return t.nvtx;
     return DDDM_ERR_BAD_ARGUMENT;
 }
 int dddm_set_trace_buffer(void* device_buffer) {

@@ -369,29 +369,35 @@ size_t dddm_backbone_scratch_bytes(int C) {
 
 int dddm_layer_norm_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
                             long N, int C, float eps, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 layer_norm_fwd f32");
     return ln_fwd<float>(x, gamma, beta, y, mean, rstd, N, C, eps, (cudaStream_t)stream);
 }
 int dddm_layer_norm_fwd_bf16(const dddm_bf16* x, const dddm_bf16* gamma, const dddm_bf16* beta, dddm_bf16* y, float* mean,
                              float* rstd, long N, int C, float eps, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 layer_norm_fwd bf16");
     return ln_fwd<bf16>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, (bf16*)y, mean, rstd, N, C, eps,
                         (cudaStream_t)stream);
 }
 int dddm_layer_norm_bwd_f32(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                             float* dx, float* dgamma, float* dbeta, float* scratch, size_t scratch_bytes, long N, int C,
                             dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 layer_norm_bwd f32");
     return ln_bwd<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, scratch, scratch_bytes, N, C, (cudaStream_t)stream);
 }
 int dddm_layer_norm_bwd_bf16(const dddm_bf16* dy, const dddm_bf16* x, const float* mean, const float* rstd,
                              const dddm_bf16* gamma, dddm_bf16* dx, dddm_bf16* dgamma, dddm_bf16* dbeta, float* scratch,
                              size_t scratch_bytes, long N, int C, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 layer_norm_bwd bf16");
     return ln_bwd<bf16>((const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)gamma, (bf16*)dx, (bf16*)dgamma,
                         (bf16*)dbeta, scratch, scratch_bytes, N, C, (cudaStream_t)stream);
 }
 int dddm_colsum_f32(const float* a, float* out, float* scratch, size_t scratch_bytes, long N, int C, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 colsum f32");
     return colsum<float>(a, out, scratch, scratch_bytes, N, C, (cudaStream_t)stream);
 }
 int dddm_colsum_bf16(const dddm_bf16* a, dddm_bf16* out, float* scratch, size_t scratch_bytes, long N, int C,
                      dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K6 colsum bf16");
     return colsum<bf16>((const bf16*)a, (bf16*)out, scratch, scratch_bytes, N, C, (cudaStream_t)stream);
 }
 

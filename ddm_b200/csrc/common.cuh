@@ -31,9 +31,28 @@ struct Tuning {
     int sthint = 0;   // ... and of the gradient stores
     int nostore = 0;  // diagnostics: pass 2 without its global stores (fp32/bf16 m = 8, 256 x 3 plan only)
     int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
+    int nvtx = -1;    // NVTX ranges around the C-ABI entry points: -1 = environment DDDM_NVTX, 0 off, 1 on
     void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)
 };
 Tuning& tuning();
+
+// ---- NVTX ranges around every C-ABI entry point (tracing), off unless DDDM_NVTX=1 or
+//      dddm_set_tuning("nvtx", 1): nsys / ncu --nvtx then show K1..K6 by name ----------------------------------
+bool nvtx_enabled();
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(nvtx_enabled()) {
+        if (on) nvtx_push(name);
+    }
+    ~NvtxRange() {
+        if (on) nvtx_pop();
+    }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define DDDM_NVTX(name) ::dddm::NvtxRange dddm_nvtx_range_(name)
 
 // ---- per-device host-side caches (a process may drive several GPUs; function attributes are per device) -------
 int device_sm_count();  // multiprocessors of the CURRENT device (api.cu)

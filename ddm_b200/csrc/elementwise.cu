@@ -486,10 +486,12 @@ extern "C" {
 
 int dddm_forward_marginal_expand_f32(const float* x0, const float* t, const float* eps, float* xt, float* xt_rep,
                                      int B, int m, long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K2 forward_marginal_expand f32");
     return forward_marginal_expand<float>(x0, t, eps, xt, xt_rep, B, m, D, (cudaStream_t)stream);
 }
 int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, dddm_bf16* xt,
                                       dddm_bf16* xt_rep, int B, int m, long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K2 forward_marginal_expand bf16");
     return forward_marginal_expand<__nv_bfloat16>((const __nv_bfloat16*)x0, t, (const __nv_bfloat16*)eps,
                                                   (__nv_bfloat16*)xt, (__nv_bfloat16*)xt_rep, B, m, D,
                                                   (cudaStream_t)stream);
@@ -498,6 +500,7 @@ int dddm_forward_marginal_expand_bf16(const dddm_bf16* x0, const float* t, const
 int dddm_forward_marginal_concat_f32(const float* x0, const float* t, const float* eps, const float* xi, void* x6,
                                      int out_dtype, float* x0_tok, int B, int m, int C, int H, int W, int patch,
                                      dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K2c forward_marginal_concat f32");
     if (out_dtype == DDDM_DTYPE_F32)
         return forward_marginal_concat<float, float>(x0, t, eps, xi, (float*)x6, x0_tok, B, m, C, H, W, patch,
                                                      (cudaStream_t)stream);
@@ -509,12 +512,14 @@ int dddm_forward_marginal_concat_f32(const float* x0, const float* t, const floa
 int dddm_forward_marginal_concat_bf16(const dddm_bf16* x0, const float* t, const dddm_bf16* eps, const dddm_bf16* xi,
                                       dddm_bf16* x6, dddm_bf16* x0_tok, int B, int m, int C, int H, int W, int patch,
                                       dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K2c forward_marginal_concat bf16");
     return forward_marginal_concat<__nv_bfloat16, __nv_bfloat16>(
         (const __nv_bfloat16*)x0, t, (const __nv_bfloat16*)eps, (const __nv_bfloat16*)xi, (__nv_bfloat16*)x6,
         (__nv_bfloat16*)x0_tok, B, m, C, H, W, patch, (cudaStream_t)stream);
 }
 
 int dddm_sigmoid_weight_sum_f32(const float* t, float bias, float* w, float* w_sum, int B, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K4 sigmoid_weight_sum");
     if (!t || (!w && !w_sum)) return DDDM_ERR_NULL_POINTER;
     if (B < 0) return DDDM_ERR_BAD_SHAPE;
     if (B == 0) {
@@ -530,12 +535,14 @@ int dddm_sigmoid_weight_sum_f32(const float* t, float bias, float* w, float* w_s
 int dddm_bridge_step_f32(float* x_out, const float* x, const float* xhat0, const float* z, const float* s,
                          const float* t, int st_is_vector, double eps_churn, float* mu_out, float* std_out, long N,
                          long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K3 bridge_step f32");
     return bridge_step<float>(x_out, x, xhat0, z, s, t, st_is_vector, eps_churn, mu_out, std_out, N, D,
                               (cudaStream_t)stream);
 }
 int dddm_bridge_step_bf16(dddm_bf16* x_out, const dddm_bf16* x, const dddm_bf16* xhat0, const dddm_bf16* z,
                           const float* s, const float* t, int st_is_vector, double eps_churn, dddm_bf16* mu_out,
                           float* std_out, long N, long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K3 bridge_step bf16");
     return bridge_step<__nv_bfloat16>((__nv_bfloat16*)x_out, (const __nv_bfloat16*)x, (const __nv_bfloat16*)xhat0,
                                       (const __nv_bfloat16*)z, s, t, st_is_vector, eps_churn, (__nv_bfloat16*)mu_out,
                                       std_out, N, D, (cudaStream_t)stream);
@@ -550,6 +557,7 @@ int dddm_bridge_step_philox_f32(float* x_out, const float* x, const float* xhat0
                                 const float* t, double eps_churn, const unsigned long long* philox_dev,
                                 unsigned long long seed, unsigned long long offset_z, unsigned long long offset_xi, long N,
                                 long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K3 bridge_step + philox f32");
     return bridge_step_philox<float>(x_out, x, xhat0, xi_next, s, t, eps_churn, philox_dev, seed, offset_z, offset_xi, N, D,
                                      (cudaStream_t)stream);
 }
@@ -557,6 +565,7 @@ int dddm_bridge_step_philox_bf16(dddm_bf16* x_out, const dddm_bf16* x, const ddd
                                  const float* s, const float* t, double eps_churn, const unsigned long long* philox_dev,
                                  unsigned long long seed, unsigned long long offset_z, unsigned long long offset_xi, long N,
                                  long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K3 bridge_step + philox bf16");
     return bridge_step_philox<__nv_bfloat16>((__nv_bfloat16*)x_out, (const __nv_bfloat16*)x, (const __nv_bfloat16*)xhat0,
                                              (__nv_bfloat16*)xi_next, s, t, eps_churn, philox_dev, seed, offset_z, offset_xi,
                                              N, D, (cudaStream_t)stream);

@@ -130,7 +130,10 @@ __device__ __forceinline__ void finish_row(const EnergyParams& p, int b, float c
         const unsigned long long packed = (unsigned long long)(__float_as_uint(conf_row) & 0x7fffffffu) |
                                           ((unsigned long long)(__float_as_uint(inter_row) & 0x7fffffffu) << 32);
         const unsigned long long prev = atomicExch(reinterpret_cast<unsigned long long*>(p.row_partials) + b, packed);
-        old = atomicAdd(p.ticket, 1u + (unsigned)(prev >> 63));
+        // acq_rel at GPU scope: the exchange above is ordered before the increment (release) and the last arriver's
+        // reads of the other rows' sums after it (acquire) by the memory model too, not only by the data dependency
+        const unsigned inc = 1u + (unsigned)(prev >> 63);
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p.ticket), "r"(inc) : "memory");
     }
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old != (unsigned)(p.B - 1)) return;

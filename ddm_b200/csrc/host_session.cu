@@ -130,6 +130,7 @@ void dddm_session_destroy(dddm_session* s) {
 
 int dddm_session_enqueue_host(dddm_session* s, const void* xhat_host, const void* x0_host, const float* t_host,
                               float w_bias, float beta, float lam, void* grad_host, float* out_host) {
+    DDDM_NVTX("dddm::session enqueue_host (H2D + K4 + K1 + D2H)");
     if (!s || !xhat_host || !x0_host || !t_host || !out_host) return DDDM_ERR_NULL_POINTER;
     SESSION_TRY(cudaSetDevice(s->device));
     auto& k = s->slot[s->next % dddm_session::kSlots];

@@ -109,6 +109,7 @@ size_t dddm_rbf_scratch_bytes(long rows, long cols) {
 int dddm_rbf_kernel_sum_f32(const float* G, long ldg, const float* a2, const float* b2, long rows, long cols, float gamma,
                             long diag_shift, int skip_diag, double* scratch, size_t scratch_bytes, double* out,
                             dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K5 rbf_kernel_sum");
     if (!G || !a2 || !b2 || !scratch || !out) return DDDM_ERR_NULL_POINTER;
     if (rows < 1 || cols < 1 || ldg < cols) return DDDM_ERR_BAD_SHAPE;
     const long gx = (cols + 1023) / 1024;

@@ -241,6 +241,7 @@ extern "C" {
 long dddm_rbf_tc_padded_cols(long D) { return D < 1 ? 0 : (D + kTileK - 1) / kTileK * kTileK; }
 
 int dddm_rbf_split_bf16(const float* x, dddm_bf16* hi, dddm_bf16* lo, long n, long D, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K5 rbf split bf16");
     if (!x || !hi || !lo) return DDDM_ERR_NULL_POINTER;
     if (n < 1 || D < 1) return DDDM_ERR_BAD_SHAPE;
     const long Dp = dddm_rbf_tc_padded_cols(D);
@@ -258,6 +259,7 @@ size_t dddm_rbf_tc_scratch_bytes(void) { return (size_t)device_sm_count() * size
 int dddm_rbf_kernel_sum_tc(const dddm_bf16* a_hi, const dddm_bf16* a_lo, const dddm_bf16* b_hi, const dddm_bf16* b_lo,
                            const float* a2, const float* b2, long rows_a, long rows_b, long D, float gamma, int symmetric,
                            double* scratch, size_t scratch_bytes, double* out, dddm_stream_t stream) {
+    DDDM_NVTX("dddm::K5 rbf_kernel_sum tcgen05");
     if (!a_hi || !a_lo || !b_hi || !b_lo || !a2 || !b2 || !scratch || !out) return DDDM_ERR_NULL_POINTER;
     if (rows_a < 1 || rows_b < 1 || D < 1 || rows_a > 2000000000L || rows_b > 2000000000L) return DDDM_ERR_BAD_SHAPE;
     if (symmetric && rows_a != rows_b) return DDDM_ERR_BAD_ARGUMENT;

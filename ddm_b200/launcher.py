@@ -464,7 +464,9 @@ def dp_parity(args, dev, world, batch_per_rank: int = 16) -> dict:
 
     flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     a = _copy.copy(args)
-    a.batch, a.synthetic, a.cuda_graph = batch_per_rank, True, True
+    a.batch, a.synthetic = batch_per_rank, True
+    if getattr(a, "cuda_graph", None) is None:
+        a.cuda_graph = True
     try:
         tr = Trainer(a, dev, world)
         x0 = tr.synthetic_batch()

@@ -34,12 +34,12 @@ def main():
     argv = ["--synthetic", "--precision", "fp32", "--grad-buckets", str(a.buckets)]
     argv += {"split": ["--cuda-graph", "--no-graph-nccl"], "graph_nccl": ["--cuda-graph", "--graph-nccl"],
              "eager": ["--no-cuda-graph"]}[a.mode]
-    args = launcher.parse_args(argv)
+    args = launcher.build_parser().parse_args(argv)
     res = {"mode": a.mode, "ranks": world, "buckets": a.buckets}
     par = launcher.dp_parity(args, dev, world)
     if rank == 0:
         res["dp_parity_fp32"] = {k: par.get(k) for k in ("loss_rel", "grad_max_rel", "grad_l2_rel", "launcher_form")}
-    args = launcher.parse_args(argv[:2] + [a.precision] + argv[3:])
+    args = launcher.build_parser().parse_args(argv[:2] + [a.precision] + argv[3:])
     thr = launcher.measure_throughput(args, dev, world, steps=a.steps, warmup=10)
     if rank == 0:
         res["dit_" + a.precision] = {k: thr[k] for k in ("img_per_s", "ms_per_step", "steps")}
