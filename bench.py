@@ -210,6 +210,10 @@ def run_reference(args) -> None:
         "config": {"workload": workload_name("f32"), "rows_per_gpu": B, "global_rows": B,
                    "parallelism": "host CPU (rank 0 only)", "l2_policy": "n/a (CPU)",
                    "launch": f"eager PyTorch + autograd on {torch.get_num_threads()} host threads",
+                   # the same key set as the GPU arm's config (the driver compares the two lines key by key)
+                   "single_stream_ms_per_step": 1e3 * dt / steps, "single_stream_rows_per_s": value,
+                   "multi_stream": {"streams": 1, "ms_per_step": 1e3 * dt / steps, "rows_per_s": value,
+                                    "note": "n/a on the CPU: one pass at a time over all host threads"},
                    "timed_region": f"exactly {steps} steps, wall clock", "kernel": "oracle/torch_port.py", "tuning": "n/a"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{steps} full fwd+bwd passes over the B={B} batch (oracle/torch_port.py, eager "

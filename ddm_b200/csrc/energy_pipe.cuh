@@ -64,9 +64,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 #define DDDM_PTRACE(slot)                                                                                     \
     do {                                                                                                      \

@@ -29,6 +29,10 @@ constexpr int kSmemMaxCluster = 8;
 constexpr int kSmemMaxChunks = 8;  // column chunks of the tile, each with its own mbarrier
 
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+constexpr float kCentredTau = 1.0f / 16.0f;  // rows with a pair closer than this (relative to the draws' distances to x0) go direct
 
 // The unit of work of a thread is a "step" of COLS consecutive columns = COLS/2 packed-fp32 pairs.
 // COLS = 4 keeps instruction count lowest (one LDS.128 per row for fp32); COLS = 2 halves the live
@@ -133,6 +137,8 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     __shared__ float s_cluster[kSmemMaxCluster][P];
     __shared__ float s_coef[P];
     __shared__ float s_val[P];
+    __shared__ unsigned char s_pi[P], s_pj[P];  // pair slot -> (i, j), filled in the prologue (before the inputs are waited for)
+    __shared__ int s_close;    // set when some pair of draws is much closer to each other than to x0 (direct pass 2)
     extern __shared__ __align__(128) unsigned char s_tile[];  // (M+1) rows x slab_vecs x 16 bytes
 
     // warps 0 .. nwarps-1 compute; the last warp is the control warp (TMA issue, cross-row reduction)
@@ -155,6 +161,16 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     // count); chunk c signals s_bar[c], so pass 1 starts on chunk 0 while the rest is still in flight.
     const int nchunks = (nv + chunk_vecs - 1) / chunk_vecs;
     const int chunk_q = chunk_vecs * U;
+    if (tid == 0) s_close = 0;
+    if (!BWD && tid >= M && tid < P) {
+        int i = 0, r = tid - M;
+        while (r >= M - 1 - i) {
+            r -= M - 1 - i;
+            ++i;
+        }
+        s_pi[tid] = (unsigned char)i;
+        s_pj[tid] = (unsigned char)(i + 1 + r);
+    }
     if (control) {  // rows of absent compute warps stay zero: the cross-warp sum always adds all 4 rows
         for (int w = nwarps; w < kSmemMaxThreads / 32; ++w)
             for (int s = lane; s < P; s += 32) s_warp[w][s] = 0.f;
@@ -224,46 +240,77 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     const float pre_pair = bwd ? 4.0f * p.g_inter[0] / (nb * (float)(M - 1))
                                : -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
-    // ---- pass 1: squared distances, COLS columns per thread per step ----
+    // ---- pass 1: squared distances, COLS columns per thread per step.  Two forms:
+    //   DIRECT   (x_i - x_j)^2 summed: 36 differences + 36 FMAs = 72 packed operations per column pair;
+    //   CENTRED  with z_i = x_i - x0 (exact): the 36 inner products z_i . z_j (8 differences + 36 FMAs = 44), and
+    //            d2_ij = |z_i|^2 + |z_j|^2 - 2 z_i . z_j afterwards.  Centred on x0 this cancels only when two draws are much
+    //            closer to each other than to the data; such rows (d2_ij < 1/16 (d2_i0 + d2_j0): error amplification <= 16,
+    //            2e-6 in fp32) are detected from the result and REDONE in the direct form from the tile in shared memory.
+    constexpr bool kCentredCapable = !BWD && LOADER == 0;
+    const bool centred1 = kCentredCapable && cluster_size == 1 && nthr >= 64;
     float2 acc2[P];
+    auto pass1 = [&](auto centred_tag) {
+        constexpr bool CENTRED = decltype(centred_tag)::value;
 #pragma unroll
-    for (int s = 0; s < P; ++s) acc2[s] = make_float2(0.f, 0.f);
-    for (int q = (control || bwd) ? nq : tid; q < nq; q += nthr) {
-        if ((q - tid) % chunk_q == 0) {  // warp-uniform: entering a new chunk
-            if constexpr (LOADER == 1) {
-                cp_async_wait_pending(window - 1);  // chunk c has landed (window groups were committed after c - 1)
-                issue_chunk((q - tid) / chunk_q + window);
-            } else {
-                mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
-            }
-            if (tid == 0 && q == 0) DDDM_TRACE(2);
-        }
-        float2 x[M + 1][NP];
-#pragma unroll
-        for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
-        lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
-#pragma unroll
-        for (int h = 0; h < NP; ++h) {
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const float2 d = sub2(x[i][h], x[M][h]);
-                acc2[i] = __ffma2_rn(d, d, acc2[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-#pragma unroll
-                for (int j = i + 1; j < M; ++j) {
-                    const float2 d = sub2(x[i][h], x[j][h]);
-                    acc2[pair_slot<M>(i, j)] = __ffma2_rn(d, d, acc2[pair_slot<M>(i, j)]);
+        for (int s = 0; s < P; ++s) acc2[s] = make_float2(0.f, 0.f);
+        for (int q = (control || bwd) ? nq : tid; q < nq; q += nthr) {
+            if ((q - tid) % chunk_q == 0) {  // warp-uniform: entering a new chunk
+                if constexpr (LOADER == 1) {
+                    cp_async_wait_pending(window - 1);  // chunk c has landed (window groups were committed after c - 1)
+                    issue_chunk((q - tid) / chunk_q + window);
+                } else {
+                    mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
                 }
+                if (tid == 0 && q == 0) DDDM_TRACE(2);
+            }
+            float2 x[M + 1][NP];
+#pragma unroll
+            for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+            lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
+#pragma unroll
+            for (int h = 0; h < NP; ++h) {
+                if constexpr (CENTRED) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        x[i][h] = sub2(x[i][h], x[M][h]);  // z_i
+                        acc2[i] = __ffma2_rn(x[i][h], x[i][h], acc2[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < M; ++j)
+                            acc2[pair_slot<M>(i, j)] = __ffma2_rn(x[i][h], x[j][h], acc2[pair_slot<M>(i, j)]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        const float2 d = sub2(x[i][h], x[M][h]);
+                        acc2[i] = __ffma2_rn(d, d, acc2[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < M; ++j) {
+                            const float2 d = sub2(x[i][h], x[j][h]);
+                            acc2[pair_slot<M>(i, j)] = __ffma2_rn(d, d, acc2[pair_slot<M>(i, j)]);
+                        }
+                }
+            }
         }
+    };
+    auto reduce_to_smem = [&]() {  // per-lane partial sums -> the warp's row of s_warp
+        float acc[WR::kPadded];
+#pragma unroll
+        for (int s = 0; s < WR::kPadded; ++s) acc[s] = (s < P) ? acc2[s < P ? s : 0].x + acc2[s < P ? s : 0].y : 0.f;
+        if (!control && !bwd) WR::run(acc, s_warp[warp], lane);
+    };
+    if constexpr (kCentredCapable) {
+        if (centred1) pass1(std::true_type{}); else pass1(std::false_type{});
+    } else {
+        pass1(std::false_type{});
     }
     if (tid == 0) DDDM_TRACE(3);
     if (tid == nthr - 32) DDDM_TRACE(11);
-    float acc[WR::kPadded];
-#pragma unroll
-    for (int s = 0; s < WR::kPadded; ++s) acc[s] = (s < P) ? acc2[s < P ? s : 0].x + acc2[s < P ? s : 0].y : 0.f;
-    if (!control && !bwd) WR::run(acc, s_warp[warp], lane);
+    reduce_to_smem();
     if (tid == 0) DDDM_TRACE(8);
     __syncthreads();
     if (tid == 0) DDDM_TRACE(9);
@@ -280,7 +327,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         cluster_arrive_release();
         cluster_wait_acquire();
     }
-    if (tid < P) {
+    auto coef_step = [&](bool from_centred) {  // executed by the threads tid < P: one distance each
         const int s = tid;
         float total = 0.f;
         if (bwd) {
@@ -290,14 +337,38 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         } else {
             total = (s_warp[0][s] + s_warp[1][s]) + (s_warp[2][s] + s_warp[3][s]);
         }
+        if constexpr (!BWD) {
+            // A pair's thread re-derives the confinement distances of its two draws from the warp partials (8 loads)
+            // instead of waiting for their threads: they turn the inner product into a distance (centred pass 1) and
+            // decide which forms the row takes (see pass 1 / pass 2).
+            if (s >= M && cluster_size == 1) {
+                const int i = s_pi[s], j = s_pj[s];
+                const float di = (s_warp[0][i] + s_warp[1][i]) + (s_warp[2][i] + s_warp[3][i]);
+                const float dj = (s_warp[0][j] + s_warp[1][j]) + (s_warp[2][j] + s_warp[3][j]);
+                if (from_centred) total = fmaxf((di + dj) - 2.0f * total, 0.f);
+                if (!(total >= kCentredTau * (di + dj))) s_close = 1;
+            }
+        }
         float val, der;
         pow_value_deriv(total, p.pw, val, der);
         s_val[s] = val;
         s_coef[s] = ((s < M) ? pre_conf : pre_pair) * der;
         if (!bwd && p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
-    }
+    };
+    if (tid < P) coef_step(centred1);
     if (tid == 0) DDDM_TRACE(10);
     __syncthreads();
+    if constexpr (kCentredCapable) {
+        if (centred1 && s_close != 0) {  // CTA-uniform: a near-duplicate pair — redo the distances in the direct form
+            if (!control) {
+                pass1(std::false_type{});
+                reduce_to_smem();
+                bar_sync_named(1, nthr);
+                if (tid < P) coef_step(false);  // nthr >= 64 > P: these are compute threads
+            }
+            bar_sync_named(2, nthr + 32);  // the control warp reads the row sums after this
+        }
+    }
     if (tid == 0) DDDM_TRACE(4);
 
     // ---- cross-row reduction: the control warp of the row's first CTA, concurrently with pass 2 ----
@@ -328,37 +399,82 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
         // grad_x0 exists only in the backward instantiation (the fused loss never differentiates w.r.t. the data)
         T* __restrict__ g0row = (BWD && p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
-        for (int q = tid; q < nq; q += nthr) {
-            if (bwd && (q - tid) % chunk_q == 0) {  // no pass 1 waited for it
-                mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+        // Pass 2 has two forms.  CENTRED (the fast one): with z_i = x_i - x0,
+        //     g_i = c_i z_i + sum_j k_ij (z_i - z_j) = (c_i + sum_j k_ij) z_i - sum_j k_ij z_j,
+        // 8 differences + 8 products + 56 FMAs = 72 packed operations per column pair instead of 100.  It cancels against
+        // |z| only (never against |x|: the differences to x0 are exact), i.e. it loses accuracy only where two draws are much
+        // closer to each other than to the data — duplicates, the identical draws of a zero-initialised output layer, where
+        // for beta < 1 the coefficient f' also explodes.  The threads that evaluate the coefficients compare every pair
+        // distance with 1/16 (d2_i0 + d2_j0) and raise s_close; such rows take the DIRECT form below (every difference
+        // x_i - x_j formed explicitly), as do the backward-only launches.
+        const bool direct = BWD || cluster_size > 1 || s_close != 0;  // (D-split clusters keep the direct form)
+        if (!direct) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // diagonal: c_i + sum_j k_ij (takes the slot of c_i)
+                float a = K2[i].x;
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    if (j != i) a += K2[pair_slot<M>(i < j ? i : j, i < j ? j : i)].x;
+                K2[i] = make_float2(a, a);
             }
-            float2 x[M + 1][NP], g[M][NP];
+            for (int q = tid; q < nq; q += nthr) {
+                float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
-            for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
-            lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
+                for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+                lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
 #pragma unroll
-            for (int h = 0; h < NP; ++h) {
+                for (int h = 0; h < NP; ++h) {
 #pragma unroll
-                for (int i = 0; i < M; ++i) g[i][h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
-                if (BWD && g0row != nullptr) {  // d/dx0 of the confinement term: -sum_i k_i (x_i - x0), fixed order
-                    float2 s0 = g[0][h];
+                    for (int i = 0; i < M; ++i) {
+                        x[i][h] = sub2(x[i][h], x[M][h]);  // z_i
+                        g[i][h] = __fmul2_rn(K2[i], x[i][h]);
+                    }
 #pragma unroll
-                    for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][h]);
-                    x[M][h] = make_float2(-s0.x, -s0.y);  // x0 is not needed below: reuse its registers
+                    for (int i = 0; i < M; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < M; ++j) {
+                            const float2 k = K2[pair_slot<M>(i, j)];
+                            const float2 nk = make_float2(-k.x, -k.y);  // folded into FFMA2's operand modifier
+                            g[i][h] = __ffma2_rn(nk, x[j][h], g[i][h]);
+                            g[j][h] = __ffma2_rn(nk, x[i][h], g[j][h]);
+                        }
                 }
 #pragma unroll
-                for (int i = 0; i < M; ++i)
-#pragma unroll
-                    for (int j = i + 1; j < M; ++j) {
-                        const float2 d = sub2(x[i][h], x[j][h]);
-                        const float2 k = K2[pair_slot<M>(i, j)];
-                        g[i][h] = __ffma2_rn(k, d, g[i][h]);
-                        g[j][h] = __ffma2_rn(make_float2(-k.x, -k.y), d, g[j][h]);
-                    }
+                for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
             }
+        } else {
+            for (int q = tid; q < nq; q += nthr) {
+                if (bwd && (q - tid) % chunk_q == 0) {  // no pass 1 waited for it
+                    mbar_wait(&s_bar[(q - tid) / chunk_q], 0);
+                }
+                float2 x[M + 1][NP], g[M][NP];
 #pragma unroll
-            for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
-            if (BWD && g0row != nullptr) stg_step<T, COLS>(g0row + (long)q * COLS, x[M]);
+                for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+                lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
+#pragma unroll
+                for (int h = 0; h < NP; ++h) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) g[i][h] = __fmul2_rn(K2[i], sub2(x[i][h], x[M][h]));
+                    if (BWD && g0row != nullptr) {  // d/dx0 of the confinement term: -sum_i k_i (x_i - x0), fixed order
+                        float2 s0 = g[0][h];
+#pragma unroll
+                        for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][h]);
+                        x[M][h] = make_float2(-s0.x, -s0.y);  // x0 is not needed below: reuse its registers
+                    }
+#pragma unroll
+                    for (int i = 0; i < M; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < M; ++j) {
+                            const float2 d = sub2(x[i][h], x[j][h]);
+                            const float2 k = K2[pair_slot<M>(i, j)];
+                            g[i][h] = __ffma2_rn(k, d, g[i][h]);
+                            g[j][h] = __ffma2_rn(make_float2(-k.x, -k.y), d, g[j][h]);
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+                if (BWD && g0row != nullptr) stg_step<T, COLS>(g0row + (long)q * COLS, x[M]);
+            }
         }
     }
     if (tid == 0) DDDM_TRACE(5);

@@ -390,6 +390,19 @@ def test_tensor_core_kernel(dev, m):
         _cabi.set_tuning("energy.variant", 0)
 
 
+@pytest.mark.parametrize("beta", [0.1, 1.0, 2.0])
+def test_centred_pass2_and_direct_fallback(dev, beta):
+    """Pass 2 of the TMA-staged kernel takes the centred form (g_i = (c_i + sum k_ij) z_i - sum k_ij z_j, z = x - x0) on
+    rows whose draws are spread and the direct-difference form on rows with near- or exact duplicates; both must hold
+    the fp32 tolerance, inside one launch that mixes such rows."""
+    m, D = 8, 3072
+    parts = [_tc_inputs(6, 16, D, r, seed=31 + k) for k, r in enumerate(("late", "mixed", "early", "dups"))]
+    xh = torch.cat([p[0][:, :m] for p in parts])  # 'mixed' keeps its near-duplicates among the first 8 draws: (2, 5), (2, 7)
+    x0 = torch.cat([p[1] for p in parts])
+    _check_case(xh.numpy(), x0.numpy(), beta, dev)
+    _check_case(xh.numpy(), x0.numpy(), beta, dev, dtype=torch.bfloat16, rel=BF16_REL)
+
+
 def test_kernel_variants_agree(dev):
     """Every launch plan (cluster size, vectors per thread, register vs smem-tile variant) is the same function."""
     from ddm_b200 import _cabi
