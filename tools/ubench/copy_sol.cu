@@ -87,7 +87,45 @@ __global__ void pull_ldg(const uint4* __restrict__ src, int nvec, long long* ns_
     if (threadIdx.x == 0) ns_out[blockIdx.x] = (long long)(t1 - t0);
 }
 
-int main() {
+// one CTA writes `bytes` from shared memory to global: 16-byte stores from `threads` threads, or `ncopies` bulk stores
+__global__ void push_stg(unsigned char* __restrict__ dst, int bytes, long long* ns_out, long cta_stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    dst += (long)blockIdx.x * cta_stride;
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(i, i, i, i);
+    __syncthreads();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + i);
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __threadfence();
+    __syncthreads();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (threadIdx.x == 0) ns_out[blockIdx.x] = (long long)(t1 - t0);
+}
+__global__ void push_bulk(unsigned char* __restrict__ dst, int bytes, int ncopies, long long* ns_out, long cta_stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    dst += (long)blockIdx.x * cta_stride;
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(i, i, i, i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const int per = bytes / ncopies;
+    for (int c = threadIdx.x; c < ncopies; c += blockDim.x) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (long)c * per),
+                     "r"((unsigned)__cvta_generic_to_shared(smem + (long)c * per)), "r"(per) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncthreads();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (threadIdx.x == 0) ns_out[blockIdx.x] = (long long)(t1 - t0);
+}
+
+int main(int argc, char** argv) {
+    const bool quick = argc > 1;
     const long read_bytes = (128L * 8 * 3072 + 128L * 3072) * 4, write_bytes = 128L * 8 * 3072 * 4;
     const int nsets = 40;
     std::vector<uint4*> in(nsets), out(nsets);
@@ -143,8 +181,8 @@ int main() {
     };
     printf("bytes per launch: read %ld + write %ld = %ld; 6452.5 GB/s -> %.2f us\n", read_bytes, write_bytes, read_bytes + write_bytes,
            (read_bytes + write_bytes) / 6452.5e3);
-    printf("cudaMemcpyAsync D2D of %ld bytes (%ld moved), one stream back to back: %.2f us\n", write_bytes, 2 * write_bytes, run(0, 0, 0, 0, true, 1));
-    for (int pdl = 0; pdl < 2; ++pdl)
+    if (!quick) printf("cudaMemcpyAsync D2D of %ld bytes (%ld moved), one stream back to back: %.2f us\n", write_bytes, 2 * write_bytes, run(0, 0, 0, 0, true, 1));
+    for (int pdl = 0; pdl < (quick ? 0 : 2); ++pdl)
         for (int grid : {148, 296, 592, 1184, 2368, 4736})
             for (int threads : {256, 512})
                 for (int unroll : {4, 8}) {
@@ -164,7 +202,7 @@ int main() {
     CK(cudaFuncSetAttribute(pull_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, tile));
     std::vector<long long> h(148);
     auto flush = [&]() { for (int s = 0; s < nsets; ++s) CK(cudaMemsetAsync(out[s], 1, write_bytes, st)); };  // 500 MB of writes: evicts the inputs
-    for (int ctas : {1, 4, 32, 128, 148}) {
+    for (int ctas : {1, 4, 32, 128}) {
         for (int ncopies : {9, 54, 216}) {
             flush();
             pull_bulk<<<ctas, 128, tile, st>>>((const unsigned char*)in[3], tile, ncopies, ns, tile);
@@ -182,6 +220,28 @@ int main() {
             std::sort(h.begin(), h.begin() + ctas);
             printf("pull 110592 B per CTA, LDG.128 x %4d threads, %3d CTAs: median %lld ns (%.1f B/ns per SM), max %lld ns\n", threads, ctas,
                    h[ctas / 2], tile / (double)h[ctas / 2], h[ctas - 1]);
+        }
+    }
+    // ---- how fast can one SM write out its 98 KB of gradient rows? ----
+    const int gtile = 98304;
+    CK(cudaFuncSetAttribute(push_stg, cudaFuncAttributeMaxDynamicSharedMemorySize, gtile));
+    CK(cudaFuncSetAttribute(push_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, gtile));
+    for (int ctas : {1, 4, 32, 128}) {
+        for (int threads : {128, 256, 512}) {
+            push_stg<<<ctas, threads, gtile, st>>>((unsigned char*)out[7], gtile, ns, gtile);
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpy(h.data(), ns, ctas * sizeof(long long), cudaMemcpyDeviceToHost));
+            std::sort(h.begin(), h.begin() + ctas);
+            printf("push 98304 B per CTA, STG.128 x %4d threads, %3d CTAs: median %lld ns (%.1f B/ns per SM), max %lld ns\n", threads, ctas,
+                   h[ctas / 2], gtile / (double)h[ctas / 2], h[ctas - 1]);
+        }
+        for (int ncopies : {8, 24, 96, 192}) {
+            push_bulk<<<ctas, 128, gtile, st>>>((unsigned char*)out[9], gtile, ncopies, ns, gtile);
+            CK(cudaStreamSynchronize(st));
+            CK(cudaMemcpy(h.data(), ns, ctas * sizeof(long long), cudaMemcpyDeviceToHost));
+            std::sort(h.begin(), h.begin() + ctas);
+            printf("push 98304 B per CTA, bulk stores x%3d, %3d CTAs: median %lld ns (%.1f B/ns per SM), max %lld ns\n", ncopies, ctas,
+                   h[ctas / 2], gtile / (double)h[ctas / 2], h[ctas - 1]);
         }
     }
     return 0;
