@@ -12,8 +12,11 @@
 //   pass 2  column owner: a thread keeps all m gradient rows of its 2 columns in registers (m float2),
 //           streams the coefficients from shared memory (LDS.128, uniform address = broadcast) and forms
 //           every difference x_i - x_j once for both rows (g_i += k d, g_j -= k d).
-// At m = 32 the path is fp32-CUDA-core bound (1.8 GFLOP per launch at B = 128, D = 3072); the direct
-// difference form is kept because the Gram form loses the fp32 tolerance.
+// At m = 32 the path is fp32-CUDA-core bound (1.8 GFLOP per launch at B = 128, D = 3072).  Like energy_smem.cuh, both
+// passes first run in the CENTRED form (z = x - x0: inner products z_i . z_j instead of squared differences in pass 1,
+// (c_i + sum_j k_ij) z_i - sum_j k_ij z_j in pass 2: one FMA per ordered pair instead of a difference and an FMA), which
+// cancels only against |z|, never against |x|; a row with a pair of draws much closer to each other than to x0 is
+// detected from the result and redone in the DIRECT forms (every difference formed explicitly).
 // Reference arithmetic: dddm/losses.py:5-25 (terms), dddm/training.py:84-85 (loss).
 #pragma once
 
@@ -51,6 +54,8 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
     __shared__ __align__(16) float s_K[M * M];   // K[i][j], j > i used
     __shared__ __align__(16) float s_A[M];       // confinement coefficients
+    __shared__ __align__(16) float s_Dg[M];      // centred pass 2: diagonal c_i + sum_j k_ij
+    __shared__ int s_close;                      // some pair of draws is much closer to each other than to x0
     __shared__ float s_val[P];
     __shared__ float s_tmp[kSmemMaxThreads / 32][64];
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -73,6 +78,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     const int nchunks = (nv + chunk_vecs - 1) / chunk_vecs;
     const int chunk_q = chunk_vecs * U;
     for (int s = tid; s < kBlkMaxSplit * P; s += blockDim.x) s_warp[s] = 0.f;
+    if (tid == 0) s_close = 0;
     if (control && lane == 0) {
         for (int c = 0; c < nchunks; ++c) {
             mbar_init(&s_bar[c], 1);
@@ -131,7 +137,9 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     constexpr int NDIAG = (NB + 1) / 2;                  // diagonal blocks are swept two at a time
     constexpr int NSWEEP = NDIAG + NB * (NB - 1) / 2;   // M = 16: 2, M = 24: 5, M = 32: 8
     const int nsplit = (NSWEEP % nwarps == 0) ? 1 : kBlkMaxSplit;  // column splits: balance the units over the warps
-    if (!control) {
+    const unsigned char* x0tile = s_tile + (size_t)M * row_bytes;
+    auto sweeps = [&](auto centred_tag) {
+        constexpr bool CENTRED = decltype(centred_tag)::value;  // accumulate z_i . z_j (z = x - x0) instead of (x_i - x_j)^2
         int waited = -1;  // chunks this thread has already waited for
         for (int unit = warp; unit < NSWEEP * nsplit; unit += nwarps) {
             const int sweep = unit / nsplit, split = unit - sweep * nsplit;
@@ -154,14 +162,28 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                         lds_step<T, COLS>(s_tile + (size_t)(rA + r) * row_bytes, q, xa[r]);
                         lds_step<T, COLS>(s_tile + (size_t)(rB + r) * row_bytes, q, xb[r]);
                     }
+                    if constexpr (CENTRED) {
+                        float2 x0v[1];
+                        lds_step<T, COLS>(x0tile, q, x0v);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            xa[r][0] = sub2(xa[r][0], x0v[0]);
+                            xb[r][0] = sub2(xb[r][0], x0v[0]);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll
                         for (int j = i + 1; j < 8; ++j) {
-                            const float2 da = sub2(xa[i][0], xa[j][0]);
-                            acc2[pair_slot<8>(i, j) - 8] = __ffma2_rn(da, da, acc2[pair_slot<8>(i, j) - 8]);
-                            const float2 db = sub2(xb[i][0], xb[j][0]);
-                            acc2[28 + pair_slot<8>(i, j) - 8] = __ffma2_rn(db, db, acc2[28 + pair_slot<8>(i, j) - 8]);
+                            if constexpr (CENTRED) {
+                                acc2[pair_slot<8>(i, j) - 8] = __ffma2_rn(xa[i][0], xa[j][0], acc2[pair_slot<8>(i, j) - 8]);
+                                acc2[28 + pair_slot<8>(i, j) - 8] = __ffma2_rn(xb[i][0], xb[j][0], acc2[28 + pair_slot<8>(i, j) - 8]);
+                            } else {
+                                const float2 da = sub2(xa[i][0], xa[j][0]);
+                                acc2[pair_slot<8>(i, j) - 8] = __ffma2_rn(da, da, acc2[pair_slot<8>(i, j) - 8]);
+                                const float2 db = sub2(xb[i][0], xb[j][0]);
+                                acc2[28 + pair_slot<8>(i, j) - 8] = __ffma2_rn(db, db, acc2[28 + pair_slot<8>(i, j) - 8]);
+                            }
                         }
                 }
                 float acc[WRD::kPadded];
@@ -189,17 +211,28 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 for (int s = 0; s < 64; ++s) acc2[s] = make_float2(0.f, 0.f);
                 for (int q = q_begin + lane; q < q_end; q += 32) {
                     for (const int c = q / chunk_q; waited < c;) mbar_wait(&s_bar[++waited], 0);
-                    float2 xi[8][1];
+                    float2 xi[8][1], x0v[1];
 #pragma unroll
                     for (int r = 0; r < 8; ++r) lds_step<T, COLS>(s_tile + (size_t)(rI + r) * row_bytes, q, xi[r]);
+                    if constexpr (CENTRED) {
+                        lds_step<T, COLS>(x0tile, q, x0v);
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) xi[r][0] = sub2(xi[r][0], x0v[0]);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {  // rows of block J are streamed one at a time (register budget)
                         float2 xj[1];
                         lds_step<T, COLS>(s_tile + (size_t)(rJ + j) * row_bytes, q, xj);
+                        if constexpr (CENTRED) {
+                            xj[0] = sub2(xj[0], x0v[0]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float2 d = sub2(xi[i][0], xj[0]);
-                            acc2[i * 8 + j] = __ffma2_rn(d, d, acc2[i * 8 + j]);
+                            for (int i = 0; i < 8; ++i) acc2[i * 8 + j] = __ffma2_rn(xi[i][0], xj[0], acc2[i * 8 + j]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 d = sub2(xi[i][0], xj[0]);
+                                acc2[i * 8 + j] = __ffma2_rn(d, d, acc2[i * 8 + j]);
+                            }
                         }
                     }
                 }
@@ -214,45 +247,73 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
         }
         // pass 2 reads every chunk: make sure this thread has observed all of them
         while (waited < nchunks - 1) mbar_wait(&s_bar[++waited], 0);
-    }
+    };
+    if (!control) sweeps(std::true_type{});
     __syncthreads();
 
     // ---- sum over column splits and over the cluster (fixed order).  Cross-CTA: every CTA folds its splits into
-    //      table 0, then PULLS its peers' tables through distributed shared memory — no staging buffer. ----
-    if (cluster_size > 1) {
-        for (int s = tid; s < P; s += blockDim.x) {
-            float t = s_warp[s];
-            for (int k = 1; k < nsplit; ++k) t += s_warp[k * P + s];
-            s_warp[s] = t;
-        }
-        cluster_wait_acquire();     // phase 0: every CTA of the cluster is running
-        cluster_arrive_release();   // phase 1: my table 0 is complete
-        cluster_wait_acquire();
-    }
+    //      table 0, then PULLS its peers' tables through distributed shared memory — no staging buffer.  Called once
+    //      (centred pass 1) and, for rows with near-duplicate draws, a second time after the direct redo. ----
     cg::cluster_group cluster = cg::this_cluster();
-    // one work item per (i, j >= i): j == i is the confinement distance of draw i
-    for (int idx = tid; idx < M * M; idx += blockDim.x) {
-        const int i = idx / M, j = idx - i * M;
-        if (j < i) continue;
-        const int s = (j == i) ? i : pair_slot<M>(i, j);
+    auto table_sum = [&](int s) {
         float total = 0.f;
         if (cluster_size > 1) {
             for (int r = 0; r < cluster_size; ++r) total += cluster.map_shared_rank(s_warp, r)[s];
         } else {
             for (int k = 0; k < nsplit; ++k) total += s_warp[k * P + s];
         }
-        float val, der;
-        pow_value_deriv(total, p.pw, val, der);
-        s_val[s] = val;
-        if (j == i) {
-            s_A[i] = pre_conf * der;
-            s_K[idx] = 0.f;
-        } else {
-            s_K[idx] = pre_pair * der;
+        return total;
+    };
+    auto exchange_and_coefs = [&](bool centred, bool first) {
+        if (cluster_size > 1) {
+            for (int s = tid; s < P; s += blockDim.x) {
+                float t = s_warp[s];
+                for (int k = 1; k < nsplit; ++k) t += s_warp[k * P + s];
+                s_warp[s] = t;
+            }
+            if (first) cluster_wait_acquire();  // phase 0: every CTA of the cluster is running
+            cluster_arrive_release();           // my table 0 is complete
+            cluster_wait_acquire();
         }
-        if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
+        // one work item per (i, j >= i): j == i is the confinement distance of draw i
+        for (int idx = tid; idx < M * M; idx += blockDim.x) {
+            const int i = idx / M, j = idx - i * M;
+            if (j < i) continue;
+            const int s = (j == i) ? i : pair_slot<M>(i, j);
+            float total = table_sum(s);
+            if (j != i) {
+                const float ni = table_sum(i), nj = table_sum(j);
+                if (centred) total = fmaxf((ni + nj) - 2.0f * total, 0.f);  // inner product -> distance
+                if (!(total >= kCentredTau * (ni + nj))) s_close = 1;        // same verdict in every CTA of the cluster
+            }
+            float val, der;
+            pow_value_deriv(total, p.pw, val, der);
+            s_val[s] = val;
+            if (j == i) {
+                s_A[i] = pre_conf * der;
+                s_K[idx] = 0.f;
+            } else {
+                s_K[idx] = pre_pair * der;
+            }
+            if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
+        }
+        if (cluster_size > 1) cluster_arrive_release();  // I no longer read my peers' tables
+        __syncthreads();
+    };
+    exchange_and_coefs(true, true);
+    const bool redo = s_close != 0;  // CTA- and cluster-uniform
+    if (redo) {
+        if (cluster_size > 1) cluster_wait_acquire();  // every peer is done with my table before it is rewritten
+        __syncthreads();
+        if (!control) sweeps(std::false_type{});
+        __syncthreads();
+        exchange_and_coefs(false, false);
+    } else if (tid < M) {  // centred pass 2: diagonal of the coefficient matrix
+        float a = s_A[tid];
+        for (int j = 0; j < M; ++j)
+            if (j != tid) a += s_K[(j > tid ? tid : j) * M + (j > tid ? j : tid)];
+        s_Dg[tid] = a;
     }
-    if (cluster_size > 1) cluster_arrive_release();  // phase 2: I no longer read my peers' tables
     __syncthreads();
 
     if (control) {
@@ -274,6 +335,44 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     if (p.grad_xhat != nullptr && nq > 0) {
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
         const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
+        if (!redo) {
+            // centred: g_i = (c_i + sum_j k_ij) z_i - sum_j k_ij z_j — one FMA per ordered pair
+            for (int q = tid; q < nq; q += nthr) {
+                float2 x[M][1], g[M][1], x0v[1];
+                lds_step<T, COLS>(x0row, q, x0v);
+#pragma unroll
+                for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
+#pragma unroll
+                for (int i0 = 0; i0 < M; i0 += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(&s_Dg[i0]);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        x[i0 + u][0] = sub2(x[i0 + u][0], x0v[0]);  // z
+                        g[i0 + u][0] = __fmul2_rn(make_float2(av[u], av[u]), x[i0 + u][0]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < M - 1; ++i) {
+#pragma unroll
+                    for (int j0 = ((i + 1) / 4) * 4; j0 < M; j0 += 4) {
+                        const float4 k4 = *reinterpret_cast<const float4*>(&s_K[i * M + j0]);
+                        const float kv[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = j0 + u;
+                            if (j <= i) continue;
+                            const float2 nk = make_float2(-kv[u], -kv[u]);
+                            g[i][0] = __ffma2_rn(nk, x[j][0], g[i][0]);
+                            g[j][0] = __ffma2_rn(nk, x[i][0], g[j][0]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+            }
+            return;
+        }
         for (int q = tid; q < nq; q += nthr) {
             float2 x[M][1], g[M][1], x0v[1];
             lds_step<T, COLS>(x0row, q, x0v);
