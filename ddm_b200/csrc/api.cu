@@ -119,9 +119,9 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     }
     if constexpr (sizeof(T) == 2) {
         // m = 16 / 32 bf16 draws: Gram + coefficient mixing on the tensor cores (takes bf16 or fp32 x0)
-        // auto: m = 32 (2.2-2.3x the blocked kernel) and every mixed-entry call; m = 16 stays on the blocked kernel, which
-        // is ahead with several launches in flight (13.9 vs 18.5 us) and level on a single one (25.3 vs 23.3 us)
-        if ((variant == 7 || (variant == 0 && (p.m == 32 || p.x0_f32))) && p.mode != kModeBwd) {
+        // auto for both: m = 32 is 2.2x the blocked kernel; m = 16 is ahead on ONE launch (19.7 vs 24.3 us: what a training
+        // step issues) and behind with several launches in flight (15.3 vs 12.5 us; energy.variant = 4 selects the blocked kernel)
+        if ((variant == 7 || variant == 0) && p.mode != kModeBwd) {
             TcPlan tp = plan_tc(p.B, p.m, p.D, (int)sizeof(T), al);
             if (tp.ok) return launch_energy_tc(p, tp, stream);
             if (variant == 7) return DDDM_ERR_UNSUPPORTED;
@@ -374,7 +374,7 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     const bool al = ((long)D * es) % 16 == 0;
     int n;
     const int variant = tuning().variant;
-    if ((variant == 7 || (variant == 0 && m == 32)) && dtype == 1) {
+    if ((variant == 7 || variant == 0) && dtype == 1) {
         TcPlan tp = plan_tc(B, m, D, es, al);
         if (tp.ok)
             return snprintf(buf, buflen, "tc<bf16,M=%d> tcgen05 gram + mixing, tma-2d sw128, 1 row per CTA, threads=320 smem=%zu", m, tp.smem_bytes);

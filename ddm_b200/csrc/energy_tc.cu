@@ -37,11 +37,11 @@ constexpr int kTcThreads = 64 + kTcWorkers;      // + TMA producer warp + MMA wa
 constexpr int kTcStageKB = 8;                    // 64-column K-blocks per pipeline stage (512 columns): few, fat stages —
                                                  // the workers' per-stage wait / fence / arrive round trip is latency, not work
 constexpr int kTcOutTiles = 3;                   // epilogue staging tiles per group (a TMA store holds its tile ~1.5 us)
-constexpr int kTcGramAccs = 4;                   // independent Gram accumulators (32 columns each), summed at read-out, so that
-                                                 // consecutive MMAs never wait for their predecessor's accumulator
+constexpr int kTcGramAccs = 2;                   // Gram accumulators (128 x 128 each), alternating so that consecutive MMAs never
+                                                 // wait for their predecessor's accumulator; summed at read-out
 constexpr int kTcAccBufs = 4;                    // gradient accumulators in TMEM (64 columns each: hi and lo products)
-constexpr int kTcGradCol0 = kTcGramAccs * 32;    // first TMEM column of the gradient accumulators
-constexpr int kTcTmemCols = 512;                 // 4 x 32 (Gram) + 4 x 64 (gradient) = 384 -> next power of two
+constexpr int kTcGradCol0 = kTcGramAccs * 128;   // first TMEM column of the gradient accumulators
+constexpr int kTcTmemCols = 512;                 // 2 x 128 (Gram) + 4 x 64 (gradient): the whole tensor memory (1 CTA per SM)
 constexpr float kTcTauDist = 1.0f / 256.0f;      // z-space: below this the Gram form of d2 is replaced by direct differences
 constexpr float kTcTauGrad = 1.0f / 65536.0f;    // x-space: below this the mixing form of the gradient is replaced too
 
@@ -58,6 +58,10 @@ struct TcCfg {
     static constexpr int kP = M + kPairs;
     static constexpr int kCoefBytes = M * M * 2;         // one bf16 coefficient matrix in core-matrix layout
     static constexpr int kItems = kTcStageKB * M * 8 / kTcWorkers;  // 16-byte chunks per worker thread and stage
+    static constexpr int kGroupKB = 128 / M;             // K-blocks one Gram instruction covers (see the MMA issuer)
+    static constexpr int kGroups = kTcStageKB / kGroupKB;  // such groups per stage
+    static_assert(kTcStageKB % kGroupKB == 0, "a stage is a whole number of Gram groups");
+    static_assert(kOut >= kGroupKB * M * (M + 1) * 4, "the partial Grams are parked in the epilogue staging tiles");
     static_assert(kOut >= 128 * 128, "slack for the 128-row operand descriptor");
 };
 
@@ -128,7 +132,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_init(&acc_empty[s], kTcWorkerWarps / 2);
         }
         mbar_init(&gram_full, 1);
-        mbar_init(&gram_empty, M / 16);  // the warps that read the Gram out of tensor memory
+        mbar_init(&gram_empty, 4);  // the four warps that read the Gram out of tensor memory
         mbar_init(&coef_ready, 1);
         fence_barrier_init();
     }
@@ -174,7 +178,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc_gram = make_instr_desc(kFmtBF16, kFmtBF16, 64, M, false, false);  // M = 64: half the operand rows
+            constexpr uint32_t idesc_gram = make_instr_desc(kFmtBF16, kFmtBF16, 128, 128, false, false);
             constexpr uint32_t idesc_grad = make_instr_desc(kFmtBF16, kFmtBF16, 128, 2 * M, true, false);
             const uint32_t cmat = smem_addr(s_cmat);
             constexpr uint32_t kCoefLbo = 128, kCoefSbo = (M / 8) * 128;  // core matrices: next 8 k / next 8 rows
@@ -188,21 +192,25 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     mbar_wait(&zfull_bar[slot], (zpar >> slot) & 1u);  // the workers have replaced x by z in this slot
                     zpar ^= 1u << slot;
                     tc_fence_after_sync();
-                    // ONE thread issues every MMA: its instruction stream is the limit for tiles this small, so the
-                    // descriptor is built once per stage and only its start-address field (bytes >> 4) is advanced
+                    // Block-diagonal batching.  A 64 x m x 16 instruction costs ~90 cycles whatever its shape (it is latency-,
+                    // not throughput-bound on the tensor pipe), and a row needs D / 16 of them.  The sub-tiles of consecutive
+                    // K-blocks are contiguous in shared memory, so a 128-row operand starting at sub-tile k covers the SAME
+                    // 16 columns-within-the-block of 128 / m consecutive K-blocks: ONE 128 x 128 x 16 instruction (A = B =
+                    // that operand) forms 128 / m Gram contributions at once on its diagonal m x m blocks (the off-diagonal
+                    // blocks mix different K-blocks and are never read).  The read-out sums the diagonal blocks.
                     const uint64_t d0 = make_desc_kmajor_sw128(smem_addr(ring + (size_t)slot * C::kStageBytes));
                     const int cnt = (dbg & 2) ? 0 : min(kTcStageKB, nkb - f * kTcStageKB);
 #pragma unroll
-                    for (int k = 0; k < kTcStageKB; ++k) {
-                        if (k < cnt) {
+                    for (int gq = 0; gq < C::kGroups; ++gq) {
+                        if (gq * C::kGroupKB < cnt) {  // (a partial group's missing sub-tiles were zeroed by the workers)
 #pragma unroll
                             for (int k4 = 0; k4 < 4; ++k4) {  // 16 columns = 32 bytes of K per instruction
-                                const uint64_t d = d0 + (uint64_t)((k * C::kSub + k4 * 32) >> 4);
-                                const int t = k * 4 + k4;  // k-step within the stage: rotates over the accumulators
-                                if (t < kTcGramAccs)
-                                    mma_f16_ss(tmem_base + (uint32_t)(t % kTcGramAccs) * 32u, d, d, idesc_gram, f != 0);
+                                const uint64_t d = d0 + (uint64_t)((gq * C::kGroupKB * C::kSub + k4 * 32) >> 4);
+                                const uint32_t acc = tmem_base + (uint32_t)(k4 % kTcGramAccs) * 128u;
+                                if (gq == 0 && k4 < kTcGramAccs)
+                                    mma_f16_ss(acc, d, d, idesc_gram, f != 0);
                                 else
-                                    mma_f16_ss(tmem_base + (uint32_t)(t % kTcGramAccs) * 32u, d, d, idesc_gram, 1);
+                                    mma_f16_ss(acc, d, d, idesc_gram, 1);
                             }
                         }
                     }
@@ -322,6 +330,9 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                             for (int e = 0; e < 8; ++e) acc_n0 = fmaf(z0[e], z0[e], acc_n0);
                         }
                         *reinterpret_cast<uint4*>(st + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    } else if (kb >= cnt && kb < (cnt + C::kGroupKB - 1) / C::kGroupKB * C::kGroupKB) {
+                        // last stage of a row whose K-blocks do not fill the Gram group: its diagonal blocks must add zero
+                        *reinterpret_cast<uint4*>(st + (uint32_t)kb * C::kSub + toff) = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
                 fence_async_smem();  // generic-proxy writes -> visible to the tensor core's reads
@@ -339,29 +350,39 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
             if (wt == 0) TC_TRACE(6);
 
-            // ---- Gram: TMEM -> shared memory (a warp that owns TMEM lanes 0..31 = Gram rows) ----
-            // (an M = 64 accumulator keeps row r in lane 32 (r / 16) + r % 16: 16 rows per warp quarter)
-            if (ww >= 2 && ww < 2 + M / 16) {  // warps 4, 5: quarters 0, 1
+            // ---- Gram: the diagonal m x m blocks of the two 128 x 128 accumulators -> shared memory -> their sum ----
+            float* s_Gp = reinterpret_cast<float*>(outs);  // [128 / m blocks][m][m + 1], parked in the (idle) staging tiles
+            if (ww < 4) {  // warps 2..5 own TMEM lane quarters 2, 3, 0, 1: accumulator rows 32 q .. 32 q + 31
                 mbar_wait(&gram_full, row_it & 1);
                 tc_fence_after_sync();
-                float gs[M];
+                float gs[32];
 #pragma unroll
-                for (int j = 0; j < M; ++j) gs[j] = 0.f;
+                for (int j = 0; j < 32; ++j) gs[j] = 0.f;
 #pragma unroll
-                for (int a = 0; a < kTcGramAccs; ++a) {  // the partial Grams, summed in a fixed order
+                for (int a = 0; a < kTcGramAccs; ++a) {
                     uint32_t v[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * 32u, v);
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * 128u + (uint32_t)quarter * 32u, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < M; ++j) gs[j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) gs[j] += __uint_as_float(v[j]);
                 }
                 tc_fence_before_sync();
-                if (lane < 16) {
+                // lane l of quarter q holds accumulator row 32 q + l, columns 32 q .. 32 q + 31: block (32 q + l) / m, row
+                // (32 q + l) % m of it, and the block's columns start at column (block * m) - 32 q of what was loaded
+                const int arow = quarter * 32 + lane, blk = arow / M, brow = arow % M, c0 = blk * M - quarter * 32;
 #pragma unroll
-                    for (int j = 0; j < M; ++j) s_G[quarter * 16 + lane][j] = gs[j];
-                }
+                for (int j = 0; j < 32; ++j)
+                    if (j >= c0 && j < c0 + M) s_Gp[(blk * M + brow) * (M + 1) + (j - c0)] = gs[j];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&gram_empty);
+            }
+            named_bar(1, kTcWorkers);
+            for (int e = wt; e < M * M; e += kTcWorkers) {  // fixed order: deterministic
+                const int i = e / M, j = e % M;
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < C::kGroupKB; ++k) t += s_Gp[(k * M + i) * (M + 1) + j];
+                s_G[i][j] = t;
             }
             named_bar(1, kTcWorkers);
             if (wt == 0) TC_TRACE(7);

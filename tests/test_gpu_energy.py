@@ -352,6 +352,7 @@ def test_tensor_core_kernel(dev, m):
     from ddm_b200 import _cabi, ops
 
     assert _cabi.describe_energy(128, 32, 3072, "bf16").startswith("tc<")  # the default plan at BASELINE config 3
+    assert _cabi.describe_energy(128, 16, 3072, "bf16").startswith("tc<") and _cabi.describe_energy(128, 16, 3072).startswith("blk<")
     try:
         _cabi.set_tuning("energy.variant", 7)
         case = 0
