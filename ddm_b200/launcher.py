@@ -512,6 +512,7 @@ def dp_parity(args, dev, world, batch_per_rank: int = 16) -> dict:
             g_ref = torch.cat([g.reshape(-1).float() for g in grads])
             if a.grad_clip is not None and a.grad_clip > 0:
                 g_ref = g_ref * (a.grad_clip / (torch.linalg.vector_norm(g_ref) + 1e-6)).clamp(max=1.0)
+            loss = loss.detach()
             out.update({
                 "loss_dp": float(loss_dp), "loss_global": float(loss),
                 "loss_rel": abs(float(loss_dp) - float(loss)) / max(abs(float(loss)), 1e-30),
