@@ -512,8 +512,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         const int dl = quarter * 32 + lane;  // column within the block
                         const float z = x0s[d0 + dl];
                         unsigned char* ot = outs + (size_t)(egroup * kTcOutTiles + (eblk % kTcOutTiles)) * C::kOutTile;
-                        if (eleader) tma_store_wait_read<kTcOutTiles - 1>();  // the store that last read this staging tile is done with it
-                        named_bar(2 + egroup, kTcWorkers / 2);
+                        // accumulator first (its TMEM read overlaps the wait for the staging tile below)
                         mbar_wait(&acc_full[buf], (g / kTcAccBufs) & 1);
                         tc_fence_after_sync();
                         // columns [0, M): x . C_hi, [M, 2M): x . C_lo
@@ -521,10 +520,12 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         const uint32_t tad = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTcGradCol0 + (uint32_t)buf * 64u;
                         tmem_ld_32x32(tad, v);
                         if (M == 32) tmem_ld_32x32(tad + 32u, w);
+                        if (eleader) tma_store_wait_read<kTcOutTiles - 1>();  // the store that last read this staging tile is done with it
                         tmem_ld_wait();
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                        named_bar(2 + egroup, kTcWorkers / 2);
 #pragma unroll
                         for (int i = 0; i < M; ++i) {
                             const float lo = (M == 32) ? __uint_as_float(w[i]) : __uint_as_float(v[(i + 16) & 31]);
