@@ -377,7 +377,8 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
     if ((variant == 7 || variant == 0) && dtype == 1) {
         TcPlan tp = plan_tc(B, m, D, es, al);
         if (tp.ok)
-            return snprintf(buf, buflen, "tc<bf16,M=%d> tcgen05 gram + mixing, tma-2d sw128, 1 row per CTA, threads=320 smem=%zu", m, tp.smem_bytes);
+            return snprintf(buf, buflen, "tc<bf16,M=%d> tcgen05 gram + mixing, tma-2d sw128, 1 row per CTA, threads=320 stages=%d smem=%zu", m,
+                            tp.stages, tp.smem_bytes);
         if (variant == 7) return snprintf(buf, buflen, "unsupported");
     }
     if (variant == 6) {

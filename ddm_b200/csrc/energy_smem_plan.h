@@ -35,6 +35,7 @@ int launch_energy_pipe(const EnergyParams& p, const PipePlan& plan, cudaStream_t
 // tensor-core kernel for m = 16, 32 bf16 draws (energy_tc.cu): Gram + coefficient mixing on tcgen05
 struct TcPlan {
     bool ok;
+    int stages;  // depth of the TMA ring (512-column stages)
     size_t smem_bytes;
 };
 TcPlan plan_tc(int B, int m, int D, int elem_size, bool aligned16);

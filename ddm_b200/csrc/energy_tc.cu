@@ -49,8 +49,7 @@ template <int M>
 struct TcCfg {
     static constexpr int kSub = M * 128;               // bytes of one K-block sub-tile (M rows x 64 bf16)
     static constexpr int kStageBytes = kTcStageKB * kSub;
-    static constexpr int kStages = (M == 32) ? 3 : 5;
-    static constexpr int kRing = kStages * kStageBytes;
+    static constexpr int kMaxStages = 6;                 // ring depth is chosen at launch from the shared memory left (3..6)
     static constexpr int kOutTile = M * 256;             // one epilogue staging tile: M draws x 128 columns bf16
     static constexpr int kOut = 2 * kTcOutTiles * kOutTile;  // two epilogue groups x kTcOutTiles; doubles as the slack the
                                                          // M = 128 Gram descriptor reads past the last sub-tile (16 KB)
@@ -86,16 +85,17 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
 
 template <int M>
 __global__ void __launch_bounds__(kTcThreads, 1)
-energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const EnergyParams p) {
+energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const EnergyParams p,
+                 const int nstages) {
     using namespace umma;
     using C = TcCfg<M>;
     constexpr int P2 = C::kPairs, P = C::kP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* outs = ring + C::kRing;                           // epilogue staging tiles [group][buffer]
+    unsigned char* outs = ring + (size_t)nstages * C::kStageBytes;   // epilogue staging tiles [group][buffer]
     float* x0s = reinterpret_cast<float*>(outs + C::kOut);           // [D] fp32 copy of the row's x0
 
-    __shared__ __align__(8) uint64_t full_bar[C::kStages], zfull_bar[C::kStages], empty_bar[C::kStages];
+    __shared__ __align__(8) uint64_t full_bar[C::kMaxStages], zfull_bar[C::kMaxStages], empty_bar[C::kMaxStages];
     __shared__ __align__(8) uint64_t acc_full[kTcAccBufs], acc_empty[kTcAccBufs];
     __shared__ __align__(8) uint64_t gram_full, gram_empty, coef_ready;
     __shared__ uint32_t tmem_slot;
@@ -122,7 +122,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_descriptor(&map_x);
         tma_prefetch_descriptor(&map_g);
-        for (int s = 0; s < C::kStages; ++s) {
+        for (int s = 0; s < nstages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&zfull_bar[s], kTcWorkerWarps);
             mbar_init(&empty_bar[s], 1);
@@ -162,8 +162,8 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
                 for (int pass = 0; pass < (want_grad ? 2 : 1); ++pass) {
                     for (int f = 0; f < nfill; ++f, ++n) {
-                        const int slot = n % C::kStages;
-                        const uint32_t phase = (n / C::kStages) & 1;
+                        const int slot = n % nstages;
+                        const uint32_t phase = (n / nstages) & 1;
                         mbar_wait(&empty_bar[slot], phase ^ 1);
                         const int kb0 = f * kTcStageKB, cnt = min(kTcStageKB, nkb - kb0);
                         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)cnt * C::kSub);
@@ -188,7 +188,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 mbar_wait(&gram_empty, (row_it & 1) ^ 1);  // the previous row's Gram has been read
                 tc_fence_after_sync();
                 for (int f = 0; f < nfill; ++f, ++n) {
-                    const int slot = n % C::kStages;
+                    const int slot = n % nstages;
                     mbar_wait(&zfull_bar[slot], (zpar >> slot) & 1u);  // the workers have replaced x by z in this slot
                     zpar ^= 1u << slot;
                     tc_fence_after_sync();
@@ -226,8 +226,8 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                 for (int ks = 0; ks < M / 16; ++ks) dcm[ks] = make_desc_kmajor_core(cmat + ks * 2 * kCoefLbo, kCoefLbo, kCoefSbo);
                 for (int f = 0; f < nfill; ++f, ++n) {
-                    const int slot = n % C::kStages;
-                    mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
+                    const int slot = n % nstages;
+                    mbar_wait(&full_bar[slot], (n / nstages) & 1);
                     const uint64_t dst0 = make_desc_mnmajor_sw128(smem_addr(ring + (size_t)slot * C::kStageBytes), C::kSub);
                     const int nblk_stage = min(kTcStageKB, nkb - f * kTcStageKB) / 2;  // blocks of 128 output columns
                     for (int h = 0; h < nblk_stage; h += 2) {  // two blocks at a time, their instructions alternating
@@ -304,9 +304,9 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             //      the pairwise distances without cancellation against |x|^2, and its diagonal IS the confinement term ----
             float acc_n2 = 0.f, acc_n0 = 0.f;
             for (int f = 0; f < nfill; ++f, ++n) {
-                const int slot = n % C::kStages;
+                const int slot = n % nstages;
                 const int kb0 = f * kTcStageKB, cnt = min(kTcStageKB, nkb - kb0);
-                mbar_wait(&full_bar[slot], (n / C::kStages) & 1);
+                mbar_wait(&full_bar[slot], (n / nstages) & 1);
                 unsigned char* st = ring + (size_t)slot * C::kStageBytes;
 #pragma unroll
                 for (int r = 0; r < ITEMS; ++r) {
@@ -613,9 +613,16 @@ TcPlan plan_tc(int B, int m, int D, int elem_size, bool aligned16) {
     TcPlan t{};
     t.ok = false;
     if (elem_size != 2 || !(m == 16 || m == 32) || B < 1 || D < 128 || D % 128 != 0 || !aligned16) return t;
-    const size_t ring = (m == 32) ? (size_t)TcCfg<32>::kRing + TcCfg<32>::kOut : (size_t)TcCfg<16>::kRing + TcCfg<16>::kOut;
-    t.smem_bytes = 1024 + ring + (size_t)D * 4;  // + the fp32 copy of the row's x0
-    if (t.smem_bytes > 232448 - 20 * 1024) return t;  // + ~18 KB of static shared memory
+    const size_t stage = (m == 32) ? (size_t)TcCfg<32>::kStageBytes : (size_t)TcCfg<16>::kStageBytes;
+    const size_t fixed = 1024 + ((m == 32) ? (size_t)TcCfg<32>::kOut : (size_t)TcCfg<16>::kOut) + (size_t)D * 4;  // + fp32 copy of x0
+    const size_t budget = 232448 - 20 * 1024;  // + ~18 KB of static shared memory
+    if (fixed + 3 * stage > budget) return t;
+    int stages = (int)((budget - fixed) / stage);
+    const int want = tuning().nv > 0 ? tuning().nv : 4;  // ("energy.nv" doubles as the ring depth knob of this kernel)
+    if (stages > want) stages = want;
+    if (stages > TcCfg<32>::kMaxStages) stages = TcCfg<32>::kMaxStages;
+    t.stages = stages;
+    t.smem_bytes = fixed + (size_t)stages * stage;
     t.ok = true;
     return t;
 }
@@ -643,11 +650,11 @@ int launch_energy_tc(const EnergyParams& p, const TcPlan& plan, cudaStream_t str
     if (p.m == 32) {
         static SmemOptIn configured;
         if (int r = configured.ensure(energy_tc_kernel<32>, plan.smem_bytes, 0)) return r;
-        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<32>, map, map_g, p);
+        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<32>, map, map_g, p, plan.stages);
     } else {
         static SmemOptIn configured;
         if (int r = configured.ensure(energy_tc_kernel<16>, plan.smem_bytes, 0)) return r;
-        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<16>, map, map_g, p);
+        e = cudaLaunchKernelEx(&cfg, energy_tc_kernel<16>, map, map_g, p, plan.stages);
     }
     count_launch();
     return (int)e;
