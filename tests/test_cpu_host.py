@@ -74,7 +74,16 @@ def test_kernel_plans(cabi):
         assert cabi.describe_energy(128, 8, 3072).startswith("reg<f32,M=8,VEC=4")
         cabi.set_tuning("energy.variant", 0)
         assert cabi.describe_energy(128, 32, 3072).startswith("blk<f32,M=32> tma-bulk")
+        # bf16 draws at m = 16 / 32 with D a multiple of 128: the tensor-core kernel; the blocked kernel otherwise / on request
+        assert cabi.describe_energy(128, 16, 3072, "bf16").startswith("tc<bf16,M=16> tcgen05")
+        assert cabi.describe_energy(128, 32, 3072, "bf16").startswith("tc<bf16,M=32> tcgen05")
+        assert cabi.describe_energy(128, 32, 12288, "bf16").startswith("tc<bf16,M=32> tcgen05")
+        assert cabi.describe_energy(128, 16, 3080, "bf16").startswith("blk<bf16,M=16> tma-bulk")
+        cabi.set_tuning("energy.variant", 4)
         assert cabi.describe_energy(128, 16, 3072, "bf16").startswith("blk<bf16,M=16> tma-bulk")
+        cabi.set_tuning("energy.variant", 6)
+        assert cabi.describe_energy(128, 8, 3072).startswith("pipe<f32,M=8> tma-bulk f32x2 rows-per-cluster=4")
+        cabi.set_tuning("energy.variant", 0)
         assert cabi.describe_energy(128, 24, 3072).startswith("blk<f32,M=24> tma-bulk")
         assert cabi.describe_energy(128, 20, 3072).startswith("tile<f32,m=20>") and "tma-bulk" in cabi.describe_energy(
             128, 20, 3072)
