@@ -224,7 +224,7 @@ class Trainer:
         self._hooks_on = False
         self._comm_stream = None
         nb = int(getattr(args, "grad_buckets", 4) or 0)
-        if world > 1 and nb > 1 and dev.type == "cuda":
+        if world > 1 and nb > 1:
             total = self.flat_grad.numel()
             bounds, owner_bucket, off, b = [0], [], 0, 0
             for prm in grad_owner:
@@ -237,7 +237,7 @@ class Trainer:
             self._buckets = [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
             self._bucket_total = [owner_bucket.count(i) for i in range(len(self._buckets))]
             self._bucket_left = list(self._bucket_total)
-            self._comm_stream = torch.cuda.Stream(dev)
+            self._comm_stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None  # CPU (gloo tests): in line
             for prm, bi in zip(grad_owner, owner_bucket):
                 prm.register_post_accumulate_grad_hook(self._make_bucket_hook(bi))
         want_graph = getattr(args, "cuda_graph", None)
@@ -276,10 +276,13 @@ class Trainer:
         """All-reduce(AVG) of one bucket on the communication stream, ordered after everything the backward has queued
         so far (all of the bucket's gradients).  Under stream capture the dependency becomes a graph edge."""
         s, e = self._buckets[bi]
-        main = torch.cuda.current_stream(self.dev)
-        self._comm_stream.wait_stream(main)
-        with torch.cuda.stream(self._comm_stream):
+        if self._comm_stream is None:
             dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+        else:
+            main = torch.cuda.current_stream(self.dev)
+            self._comm_stream.wait_stream(main)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(self.flat_grad[s:e], op=dist.ReduceOp.AVG)
         self._bucket_left[bi] = -1  # done
 
     def _fwd_bwd(self, x0: torch.Tensor, overlap: bool = False, **kw) -> torch.Tensor:
@@ -297,7 +300,8 @@ class Trainer:
             for bi, left in enumerate(self._bucket_left):  # parameters without a gradient this step: reduce what is left
                 if left >= 0:
                     self._reduce_bucket(bi)
-            torch.cuda.current_stream(self.dev).wait_stream(self._comm_stream)
+            if self._comm_stream is not None:
+                torch.cuda.current_stream(self.dev).wait_stream(self._comm_stream)
         else:
             loss.backward()
             if overlap and self.world > 1:

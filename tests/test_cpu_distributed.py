@@ -103,16 +103,22 @@ def _tiny_model():
     return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3))
 
 
-def _trainer_worker(rank: int, world: int, port: int, out_dir: str):
+def _trainer_worker(rank: int, world: int, port: int, out_dir: str, buckets: int = 4):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from ddm_b200 import launcher
 
-        args = launcher.build_parser().parse_args(["--precision", "fp32", "--grad-clip", "0.05", "--lr", "1e-2"])
+        args = launcher.build_parser().parse_args(["--precision", "fp32", "--grad-clip", "0.05", "--lr", "1e-2",
+                                                   "--grad-buckets", str(buckets)])
         torch.manual_seed(0 if rank == 0 else 1234)  # only rank 0's initial weights may matter (broadcast at init)
         tr = launcher.Trainer(args, torch.device("cpu"), world, module=_tiny_model(), loss_fn=_tiny_loss)
         assert not tr.use_graph
+        # the flat gradient goes in contiguous buckets, each all-reduced from a backward hook when its last gradient exists
+        assert len(tr._buckets) == (min(buckets, 4) if buckets > 1 else 0)  # 4 parameter tensors: at most 4 buckets
+        if tr._buckets:
+            assert tr._buckets[0][0] == 0 and tr._buckets[-1][1] == tr.flat_grad.numel()
+            assert all(a[1] == b[0] for a, b in zip(tr._buckets, tr._buckets[1:])) and sum(tr._bucket_total) == 4
         gen = torch.Generator().manual_seed(1)
         data = torch.randn(4, 8, 6, generator=gen)  # 4 steps of a global batch of 8
         per = 8 // world
@@ -130,11 +136,13 @@ def _trainer_worker(rank: int, world: int, port: int, out_dir: str):
         dist.destroy_process_group()
 
 
-def test_trainer_flat_allreduce_clip_matches_single_process(tmp_path):
-    """Flat-buffer all-reduce(AVG) + device-side global-norm clip + AdamW over 2 ranks == the reference recipe
-    (zero_grad -> backward -> clip_grad_norm_ -> AdamW.step, train_cifar10_dit.py:152-169) on the global batch."""
+@pytest.mark.parametrize("buckets", [4, 2, 0])
+def test_trainer_flat_allreduce_clip_matches_single_process(tmp_path, buckets):
+    """Flat-buffer all-reduce(AVG) — as ONE collective or in hook-launched buckets — + device-side global-norm clip + AdamW
+    over 2 ranks == the reference recipe (zero_grad -> backward -> clip_grad_norm_ -> AdamW.step,
+    train_cifar10_dit.py:152-169) on the global batch."""
     world = 2
-    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_trainer_worker, args=(world, _free_port(), str(tmp_path), buckets), nprocs=world, join=True)
     flat = torch.load(tmp_path / "flat.pt")
     torch.manual_seed(0)  # Trainer seeds the initial weights with args.seed = 0
     model = _tiny_model()
