@@ -357,26 +357,27 @@ __device__ __forceinline__ void normal4(unsigned long long seed, unsigned long l
 
 // philox = {seed, offset of the z draw, offset of the xi draw} (device memory, so that a captured graph can be
 // replayed with new offsets), or null with the three values passed by value.
-template <typename T>
+// IDX = unsigned (the whole lattice below 2^31 work items and elements: one 32-bit division per work item) or long.
+template <typename T, typename IDX>
 __global__ void __launch_bounds__(256)
 bridge_step_philox_kernel(T* x_out, const T* x, const T* xhat0, T* xi_out, const float* __restrict__ s,
                           const float* __restrict__ t, float e2, float ome2, const unsigned long long* __restrict__ philox,
-                          unsigned long long seed, unsigned long long off_z, unsigned long long off_xi, long G, int iters,
-                          long numel) {
+                          unsigned long long seed, unsigned long long off_z, unsigned long long off_xi, IDX G, int iters,
+                          IDX numel) {
     if (philox != nullptr) {
         seed = philox[0];
         off_z = philox[1];
         off_xi = philox[2];
     }
     const BridgeCoef c = bridge_coef(s[0], t[0], e2, ome2);
-    const long total = G * iters;
-    for (long w = (long)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
-        const long it = w / G, v = w - it * G;
-        const long li0 = v + 4 * G * it;
+    const IDX total = G * (IDX)iters;
+    for (IDX w = (IDX)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (IDX)gridDim.x * blockDim.x) {
+        const IDX it = w / G, v = w - it * G;
+        const IDX li0 = v + 4 * G * it;
         float xv[4], hv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const long li = li0 + G * k;
+            const IDX li = li0 + G * k;
             if (li < numel) {
                 xv[k] = Elem<T>::to_float(x[li]);
                 hv[k] = Elem<T>::to_float(xhat0[li]);
@@ -386,7 +387,7 @@ bridge_step_philox_kernel(T* x_out, const T* x, const T* xhat0, T* xi_out, const
         normal4(seed, off_z / 4 + (unsigned long long)it, (unsigned long long)v, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const long li = li0 + G * k;
+            const IDX li = li0 + G * k;
             if (li < numel) {
                 const float mu = __fadd_rn(__fmul_rn(c.c_xt, xv[k]), __fmul_rn(c.c_x0, hv[k]));
                 const float zk = Elem<T>::to_float(Elem<T>::from_float(z[k]));  // randn_like(x) has x's dtype
@@ -398,7 +399,7 @@ bridge_step_philox_kernel(T* x_out, const T* x, const T* xhat0, T* xi_out, const
             normal4(seed, off_xi / 4 + (unsigned long long)it, (unsigned long long)v, xi);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const long li = li0 + G * k;
+                const IDX li = li0 + G * k;
                 if (li < numel) xi_out[li] = Elem<T>::from_float(xi[k]);
             }
         }
@@ -432,12 +433,26 @@ static int bridge_step_philox(T* x_out, const T* x, const T* xhat0, T* xi_out, c
     long G, iters;
     torch_philox_plan(numel, &G, &iters);
     const long total = G * iters;
+    // one resident wave: the kernel is bound by the Philox rounds and Box-Muller, not by memory, so tails cost
+    static int resident_per_device[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    if (resident_per_device[dev] == 0) {
+        int r = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, bridge_step_philox_kernel<T, unsigned>, 256, 0);
+        resident_per_device[dev] = r > 0 ? r : 4;
+    }
     long blocks = (total + 255) / 256;
-    const long cap = (long)num_sms() * 8;
+    const long cap = (long)num_sms() * resident_per_device[dev];
     if (blocks > cap) blocks = cap;
     const float e2 = (float)(eps_churn * eps_churn), ome2 = (float)(1.0 - eps_churn * eps_churn);
-    bridge_step_philox_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(x_out, x, xhat0, xi_out, s, t, e2, ome2, philox_dev,
-                                                                        seed, off_z, off_xi, G, (int)iters, numel);
+    if (total * 5 < (1L << 31) && numel < (1L << 31))  // 4 G it + 3 G stays below 2^31 as well
+        bridge_step_philox_kernel<T, unsigned><<<(unsigned)blocks, 256, 0, stream>>>(
+            x_out, x, xhat0, xi_out, s, t, e2, ome2, philox_dev, seed, off_z, off_xi, (unsigned)G, (int)iters, (unsigned)numel);
+    else
+        bridge_step_philox_kernel<T, long><<<(unsigned)blocks, 256, 0, stream>>>(x_out, x, xhat0, xi_out, s, t, e2, ome2, philox_dev,
+                                                                                  seed, off_z, off_xi, G, (int)iters, numel);
     count_launch();
     return (int)cudaGetLastError();
 }
