@@ -341,10 +341,18 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
             // A pair's thread re-derives the confinement distances of its two draws from the warp partials (8 loads)
             // instead of waiting for their threads: they turn the inner product into a distance (centred pass 1) and
             // decide which forms the row takes (see pass 1 / pass 2).
-            if (s >= M && cluster_size == 1) {
+            if (s >= M) {
                 const int i = s_pi[s], j = s_pj[s];
-                const float di = (s_warp[0][i] + s_warp[1][i]) + (s_warp[2][i] + s_warp[3][i]);
-                const float dj = (s_warp[0][j] + s_warp[1][j]) + (s_warp[2][j] + s_warp[3][j]);
+                float di = 0.f, dj = 0.f;
+                if (cluster_size > 1) {  // D-split rows: the same sums in every CTA of the cluster, hence the same verdict
+                    for (int r = 0; r < cluster_size; ++r) {
+                        di += s_cluster[r][i];
+                        dj += s_cluster[r][j];
+                    }
+                } else {
+                    di = (s_warp[0][i] + s_warp[1][i]) + (s_warp[2][i] + s_warp[3][i]);
+                    dj = (s_warp[0][j] + s_warp[1][j]) + (s_warp[2][j] + s_warp[3][j]);
+                }
                 if (from_centred) total = fmaxf((di + dj) - 2.0f * total, 0.f);
                 if (!(total >= kCentredTau * (di + dj))) s_close = 1;
             }
@@ -407,7 +415,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         // for beta < 1 the coefficient f' also explodes.  The threads that evaluate the coefficients compare every pair
         // distance with 1/16 (d2_i0 + d2_j0) and raise s_close; such rows take the DIRECT form below (every difference
         // x_i - x_j formed explicitly), as do the backward-only launches.
-        const bool direct = BWD || cluster_size > 1 || s_close != 0;  // (D-split clusters keep the direct form)
+        const bool direct = BWD || s_close != 0;
         if (!direct) {
 #pragma unroll
             for (int i = 0; i < M; ++i) {  // diagonal: c_i + sum_j k_ij (takes the slot of c_i)
