@@ -120,8 +120,11 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {
 //           the HBM-bound load phase.  The slots are thread-private: no barrier between the copy and its use.
 // X0F32 (bf16 draws only): x0 stays fp32 in memory and in the tile — the mixed entry point a bf16 backbone uses
 //           (bf16 xhat in, fp32 data, bf16 gradient out), so that neither xhat is up-converted nor x0 rounded.
-template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false, int LOADER = 0, bool X0F32 = false>
-__global__ void __launch_bounds__(kSmemMaxThreads + 32, MIN_CTAS)
+// NW: compute warps the instantiation is built for (4 = one per SM sub-partition, two CTAs of different launches per SM;
+// 8 = one CTA per SM, for launches whose rows fit one wave: pass 1 runs in the shadow of the load phase only while data
+// keeps arriving, and what is left of it after the last chunk has landed is halved).
+template <typename T, int M, int COLS, int MIN_CTAS, bool BWD = false, int LOADER = 0, bool X0F32 = false, int NW = 4>
+__global__ void __launch_bounds__(NW * 32 + 32, MIN_CTAS)
 energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cluster_size, const int chunk_vecs) {
     namespace cg = cooperative_groups;
     constexpr int P = M * (M + 1) / 2;
@@ -133,7 +136,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     constexpr int NP = Step<T, COLS>::kPairs;
     using WR = WarpReduce<P>;
     __shared__ __align__(8) uint64_t s_bar[kSmemMaxChunks];
-    __shared__ float s_warp[kSmemMaxThreads / 32][P];
+    __shared__ float s_warp[NW][P];
     __shared__ float s_cluster[kSmemMaxCluster][P];
     __shared__ float s_coef[P];
     __shared__ float s_val[P];
@@ -172,7 +175,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         s_pj[tid] = (unsigned char)(i + 1 + r);
     }
     if (control) {  // rows of absent compute warps stay zero: the cross-warp sum always adds all 4 rows
-        for (int w = nwarps; w < kSmemMaxThreads / 32; ++w)
+        for (int w = nwarps; w < NW; ++w)
             for (int s = lane; s < P; s += 32) s_warp[w][s] = 0.f;
     }
     if (LOADER == 0 && control && lane == 0) {
@@ -316,12 +319,17 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
     if (tid == 0) DDDM_TRACE(9);
 
     // ---- cross-warp and cross-CTA sums, fixed order; one thread per distance ----
-    static_assert(kSmemMaxThreads / 32 == 4, "fixed 4-row cross-warp sum");
+    static_assert(NW == 4 || NW == 8, "fixed-shape cross-warp sum");
+    auto rows_sum = [&](int s) {  // the warps' partial sums of slot s, in a fixed tree
+        float t = (s_warp[0][s] + s_warp[1][s]) + (s_warp[2][s] + s_warp[3][s]);
+        if constexpr (NW == 8) t += (s_warp[4][s] + s_warp[5][s]) + (s_warp[6][s] + s_warp[7][s]);
+        return t;
+    };
     if (cluster_size > 1) {
         cg::cluster_group cluster = cg::this_cluster();
         cluster_wait_acquire();  // phase 0 complete: every CTA of the cluster is running
         if (tid < P) {
-            const float t = (s_warp[0][tid] + s_warp[1][tid]) + (s_warp[2][tid] + s_warp[3][tid]);
+            const float t = rows_sum(tid);
             for (int r = 0; r < cluster_size; ++r) cluster.map_shared_rank(&s_cluster[0][0], r)[rank * P + tid] = t;
         }
         cluster_arrive_release();
@@ -335,7 +343,7 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
         } else if (cluster_size > 1) {
             for (int r = 0; r < cluster_size; ++r) total += s_cluster[r][s];
         } else {
-            total = (s_warp[0][s] + s_warp[1][s]) + (s_warp[2][s] + s_warp[3][s]);
+            total = rows_sum(s);
         }
         if constexpr (!BWD) {
             // A pair's thread re-derives the confinement distances of its two draws from the warp partials (8 loads)
@@ -350,8 +358,8 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
                         dj += s_cluster[r][j];
                     }
                 } else {
-                    di = (s_warp[0][i] + s_warp[1][i]) + (s_warp[2][i] + s_warp[3][i]);
-                    dj = (s_warp[0][j] + s_warp[1][j]) + (s_warp[2][j] + s_warp[3][j]);
+                    di = rows_sum(i);
+                    dj = rows_sum(j);
                 }
                 if (from_centred) total = fmaxf((di + dj) - 2.0f * total, 0.f);
                 if (!(total >= kCentredTau * (di + dj))) s_close = 1;

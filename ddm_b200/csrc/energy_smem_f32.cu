@@ -21,7 +21,8 @@ SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows) {
     const size_t smem = (size_t)(m + x0_rows) * slab * 16;  // x0_rows = 2: fp32 x0 next to bf16 draws (mixed entry)
     if (smem > 200 * 1024) return s;  // slab too wide: the chunked tile kernel handles it
     int threads = t.threads;
-    if (threads < 32 || threads > kSmemMaxThreads || threads % 32) {
+    // up to 256 compute threads on request (m = 8, one CTA per SM: tuning "energy.threads" = 256)
+    if (threads < 32 || threads > (m == 8 && cluster == 1 ? 2 * kSmemMaxThreads : kSmemMaxThreads) || threads % 32) {
         threads = (int)((slab + 31) / 32 * 32);  // auto: 128 compute threads, fewer for narrow slabs
         if (threads > 128) threads = 128;
         if (threads < 32) threads = 32;

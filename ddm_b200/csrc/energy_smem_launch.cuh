@@ -39,7 +39,16 @@ int launch_energy_smem_m(const EnergyParams& p, const SmemPlan& plan, cudaStream
             which = 2;
         }
     }
-    static SmemOptIn configured[6];  // per instantiation and per device
+    if (plan.threads > kSmemMaxThreads) {  // 8 compute warps, one CTA per SM (single-wave launches; fused loss / split forward)
+        if (which != 0 || p.mode == kModeBwd) return DDDM_ERR_UNSUPPORTED;
+        if constexpr (M == 8) {
+            kernel = energy_fused_smem_kernel<T, M, kCols, 1, false, 0, false, 8>;
+            which = 6;
+        } else {
+            return DDDM_ERR_UNSUPPORTED;
+        }
+    }
+    static SmemOptIn configured[7];  // per instantiation and per device
     if (int e = configured[which].ensure(kernel, plan.smem_bytes, 40 * 1024)) return e;
     // the backward needs no cross-CTA sum: same grid, but the D-slabs of a row run as independent CTAs
     const int cluster = (p.mode == kModeBwd) ? 1 : plan.cluster;

@@ -431,6 +431,18 @@ def test_kernel_variants_agree(dev):
                         seen.add(_cabi.describe_energy(16, 8, 3072))
                         assert abs(out[0] - loss) <= 2e-5 * abs(conf), (variant, cluster, nv, loader)
                         assert _rel(g, grad) <= FP32_REL, (variant, cluster, nv, loader, _rel(g, grad))
+        # the 8-compute-warp build of the TMA-staged kernel (one CTA per SM; opt-in: "energy.threads" = 256)
+        _cabi.set_tuning("energy.variant", 3)
+        _cabi.set_tuning("energy.cluster", 0)
+        _cabi.set_tuning("energy.loader", 0)
+        for nv in (1, 2):
+            _cabi.set_tuning("energy.threads", 256)
+            _cabi.set_tuning("energy.nv", nv)
+            assert "threads=256" in _cabi.describe_energy(16, 8, 3072)
+            out, g = _fused(xh, x0, 0.5, 0.1, 1.0)
+            seen.add(_cabi.describe_energy(16, 8, 3072))
+            assert abs(out[0] - loss) <= 2e-5 * abs(conf) and _rel(g, grad) <= FP32_REL, ("threads=256", nv, _rel(g, grad))
+        _cabi.set_tuning("energy.threads", 0)
         for pdl in (0, 1):
             _cabi.set_tuning("energy.variant", 0)
             _cabi.set_tuning("energy.cluster", 0)
