@@ -431,6 +431,22 @@ def test_sampler_fused_noise_equals_reference_draw_order(dev):
                 assert torch.equal(tail, tail_ref), (shape, graph, fused)
 
 
+def test_nvtx_ranges_toggle(dev):
+    """NVTX ranges around the C-ABI entry points (tracing) can be switched on and off at run time; with no
+    profiler attached they are no-ops and results do not change."""
+    from ddm_b200 import _cabi, ops
+
+    t = torch.rand(64, device=dev)
+    base = ops.sigmoid_weight_sum(t, 0.0)[1].clone()
+    try:
+        _cabi.set_tuning("nvtx", 1)
+        assert _cabi.get_tuning("nvtx") == 1
+        assert torch.equal(ops.sigmoid_weight_sum(t, 0.0)[1], base)
+    finally:
+        _cabi.set_tuning("nvtx", 0)
+    assert _cabi.get_tuning("nvtx") == 0
+
+
 def test_sampler_cuda_graph_equals_eager(dev):
     """sample_dddm(cuda_graph=True): same Philox stream, same draws, same result as the eager loop."""
     import ddm_b200
