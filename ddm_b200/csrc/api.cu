@@ -220,6 +220,19 @@ static int energy_terms_bwd(const T* xhat, const T* x0, const float* dist, const
     p.mode = kModeTerms;
     const bool al = is_aligned16(xhat) && is_aligned16(x0) && is_aligned16(grad_xhat) &&
                     (!grad_x0 || is_aligned16(grad_x0)) && ((long)D * (long)sizeof(T)) % 16 == 0;
+    if constexpr (sizeof(T) == 2) {
+        // m = 16 / 32 bf16 draws: the tensor-core kernel in backward mode (coefficient mixing from the saved distances)
+        if (tuning().variant == 0 || tuning().variant == 7) {
+            TcPlan tp = plan_tc(B, m, D, (int)sizeof(T), al);
+            if (tp.ok) {
+                p.mode = kModeBwd;
+                p.trace = static_cast<unsigned long long*>(tuning().trace);
+                p.ld_hint = tuning().ldhint;
+                return launch_energy_tc(p, tp, stream);
+            }
+            if (tuning().variant == 7) return DDDM_ERR_UNSUPPORTED;
+        }
+    }
     if (tuning().variant == 0 || tuning().variant == 3) {
         // TMA-staged packed-fp32 kernel in backward mode (pass 2 only, coefficients from the saved distances)
         SmemPlan sp = plan_smem(m, D, (int)sizeof(T), al);

@@ -23,6 +23,11 @@
 // recomputed by direct differences, their coefficients are left out of C and their gradient contribution is added by
 // a direct-difference post-pass — exact duplicates give (1e-12)^(beta/2) and zero gradient like the reference.
 //
+// Backward-only launches (kModeBwd: the autograd backward of `generalized_energy_terms`, losses.py:5-25) reuse the kernel:
+// the distances come from the forward's saved `dist`, pass 1 only measures |x_i|^2 for the flags (no Gram), the prefactors
+// are the two upstream gradients, and grad_x0 = - sum_i grad_xhat_i falls out of the epilogue (the pair terms are
+// antisymmetric: their sum over the draws vanishes, what is left is minus the confinement gradients).
+//
 // Reference: dddm/losses.py:5-25, dddm/training.py:84-85.
 #include "energy.cuh"
 #include "energy_smem_plan.h"
@@ -117,6 +122,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int nkb = D / 64;                                  // K-blocks per row
     const int nfill = (nkb + kTcStageKB - 1) / kTcStageKB;   // stage fills per pass
     const bool want_grad = p.grad_xhat != nullptr;
+    const bool bwd = p.mode == kModeBwd;  // distances given, no loss outputs, grad_x0 on request
     const int dbg = p.ld_hint;  // diagnostics (tuning "energy.ldhint"): 1 no transform, 2 no Gram MMAs, 4 no gradient MMAs, 8 no stores
 
     if (threadIdx.x == 0) {
@@ -199,7 +205,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     // that operand) forms 128 / m Gram contributions at once on its diagonal m x m blocks (the off-diagonal
                     // blocks mix different K-blocks and are never read).  The read-out sums the diagonal blocks.
                     const uint64_t d0 = make_desc_kmajor_sw128(smem_addr(ring + (size_t)slot * C::kStageBytes));
-                    const int cnt = (dbg & 2) ? 0 : min(kTcStageKB, nkb - f * kTcStageKB);
+                    const int cnt = ((dbg & 2) || bwd) ? 0 : min(kTcStageKB, nkb - f * kTcStageKB);
 #pragma unroll
                     for (int gq = 0; gq < C::kGroups; ++gq) {
                         if (gq * C::kGroupKB < cnt) {  // (a partial group's missing sub-tiles were zeroed by the workers)
@@ -274,6 +280,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const bool x0f = p.x0_f32 != 0;
         uint32_t n = 0, g = 0, row_it = 0, eblk = 0;  // eblk: blocks this epilogue group has staged (staging-buffer parity)
         for (int b = blockIdx.x; b < p.B; b += gridDim.x, ++row_it) {
+            const long x0_base = (long)b * D;
             // ---- stage x0 as fp32 (bf16 or fp32 in memory) ----
             if (x0f) {
                 const float* src = static_cast<const float*>(p.x0) + (long)b * D;
@@ -297,8 +304,9 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             named_bar(1, kTcWorkers);
             const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
             const float nb = (float)p.B * (float)M;
-            const float pre_conf = 2.0f * W / nb;
-            const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
+            const float pre_conf = bwd ? 2.0f * p.g_conf[0] / nb : 2.0f * W / nb;
+            const float pre_pair = bwd ? 4.0f * p.g_inter[0] / (nb * (float)(M - 1))
+                                       : -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
             // ---- pass 1 (workers): x -> z = bf16(x - x0) in place (same swizzled position): centred on x0 the Gram keeps
             //      the pairwise distances without cancellation against |x|^2, and its diagonal IS the confinement term ----
@@ -329,7 +337,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
                             for (int e = 0; e < 8; ++e) acc_n0 = fmaf(z0[e], z0[e], acc_n0);
                         }
-                        *reinterpret_cast<uint4*>(st + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        if (!bwd) *reinterpret_cast<uint4*>(st + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                     } else if (kb >= cnt && kb < (cnt + C::kGroupKB - 1) / C::kGroupKB * C::kGroupKB) {
                         // last stage of a row whose K-blocks do not fill the Gram group: its diagonal blocks must add zero
                         *reinterpret_cast<uint4*>(st + (uint32_t)kb * C::kSub + toff) = make_uint4(0u, 0u, 0u, 0u);
@@ -387,17 +395,22 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             named_bar(1, kTcWorkers);
             if (wt == 0) TC_TRACE(7);
 
-            // ---- distances in z-space: conf = diagonal; pairs G_ii + G_jj - 2 G_ij, near-duplicates by direct differences ----
-            if (wt < M) s_d2[wt] = fmaxf(s_G[wt][wt], 0.f);
-            for (int s = wt; s < P2; s += kTcWorkers) {
-                const int i = s_pi[s], j = s_pj[s];
-                const float nn = s_G[i][i] + s_G[j][j];
-                const float d2 = nn - 2.0f * s_G[i][j];
-                if (!(d2 >= kTcTauDist * nn)) {  // also catches NaN
-                    const int k = atomicAdd(&s_nflag, 1);
-                    s_flag[k] = (unsigned short)s;
-                } else {
-                    s_d2[M + s] = d2;
+            // ---- distances in z-space: conf = diagonal; pairs G_ii + G_jj - 2 G_ij, near-duplicates by direct differences
+            //      (backward-only launches take the forward's saved distances) ----
+            if (bwd) {
+                for (int s = wt; s < P; s += kTcWorkers) s_d2[s] = p.dist[(long)b * P + s];
+            } else {
+                if (wt < M) s_d2[wt] = fmaxf(s_G[wt][wt], 0.f);
+                for (int s = wt; s < P2; s += kTcWorkers) {
+                    const int i = s_pi[s], j = s_pj[s];
+                    const float nn = s_G[i][i] + s_G[j][j];
+                    const float d2 = nn - 2.0f * s_G[i][j];
+                    if (!(d2 >= kTcTauDist * nn)) {  // also catches NaN
+                        const int k = atomicAdd(&s_nflag, 1);
+                        s_flag[k] = (unsigned short)s;
+                    } else {
+                        s_d2[M + s] = d2;
+                    }
                 }
             }
             named_bar(1, kTcWorkers);
@@ -441,7 +454,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 s_val[s] = val;
                 const float coef = ((s < M) ? pre_conf : pre_pair) * der;
                 s_coef[s] = coef;
-                if (p.dist != nullptr) p.dist[(long)b * P + s] = d2;
+                if (p.dist != nullptr && !bwd) p.dist[(long)b * P + s] = d2;
                 if (want_grad) {
                     if (s < M) {
                         const bool fl = !(d2 >= kTcTauGrad * (s_n2[s] + s_n2[M]));
@@ -486,7 +499,7 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (wt == 0) TC_TRACE(8);
 
             // ---- row sums -> loss (one warp; the others go on) ----
-            if (ww == 7) {
+            if (ww == 7 && !bwd) {
                 float c = 0.f, it = 0.f;
                 for (int s = lane; s < P; s += 32) {
                     if (s < M) c += s_val[s]; else it += s_val[s];
@@ -526,12 +539,17 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
                         named_bar(2 + egroup, kTcWorkers / 2);
+                        float gsum = 0.f;
 #pragma unroll
                         for (int i = 0; i < M; ++i) {
                             const float lo = (M == 32) ? __uint_as_float(w[i]) : __uint_as_float(v[(i + 16) & 31]);
                             const float o = fmaf(cneg[i], z, __uint_as_float(v[i]) + lo);
+                            gsum += o;
                             *reinterpret_cast<__nv_bfloat16*>(ot + i * 256 + dl * 2) = __float2bfloat16_rn(o);
                         }
+                        // d/dx0 = - sum_i d/dxhat_i: the pair terms cancel in the sum, the confinement terms change sign
+                        if (bwd && p.grad_x0 != nullptr)
+                            static_cast<__nv_bfloat16*>(p.grad_x0)[x0_base + d0 + dl] = __float2bfloat16_rn(-gsum);
                         fence_async_smem();
                         named_bar(2 + egroup, kTcWorkers / 2);
                         if (eleader && !(dbg & 8)) {
@@ -595,6 +613,31 @@ energy_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     }
                 }
             }
+            if (want_grad && bwd && p.grad_x0 != nullptr && s_cflag != 0) {
+                // confinement terms that went through the direct post-pass also belong in grad_x0 (one warp, all of them)
+                named_bar(1, kTcWorkers);
+                if (ww == 0) {
+                    __nv_bfloat16* g0 = static_cast<__nv_bfloat16*>(p.grad_x0) + x0_base;
+                    for (int d = lane * 8; d < D; d += 256) {
+                        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        for (int i = 0; i < M; ++i) {
+                            if (!((s_cflag >> i) & 1u)) continue;
+                            const float k = s_coef[i];
+                            float xv[8];
+                            unpack8(*reinterpret_cast<const uint4*>(xrow0 + ((long)b * M + i) * D + d), xv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) a[e] = fmaf(k, xv[e] - x0s[d + e], a[e]);
+                        }
+                        uint4 gq;
+                        asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(gq.x), "=r"(gq.y), "=r"(gq.z), "=r"(gq.w) : "l"(g0 + d));
+                        gq.x = pack_bf16x2(bf16lo(gq.x) - a[0], bf16hi(gq.x) - a[1]);
+                        gq.y = pack_bf16x2(bf16lo(gq.y) - a[2], bf16hi(gq.y) - a[3]);
+                        gq.z = pack_bf16x2(bf16lo(gq.z) - a[4], bf16hi(gq.z) - a[5]);
+                        gq.w = pack_bf16x2(bf16lo(gq.w) - a[6], bf16hi(gq.w) - a[7]);
+                        *reinterpret_cast<uint4*>(g0 + d) = gq;
+                    }
+                }
+            }
             if (wt == 0) TC_TRACE(10);
             named_bar(1, kTcWorkers);  // x0s, s_* are rewritten by the next row
         }
@@ -628,7 +671,7 @@ TcPlan plan_tc(int B, int m, int D, int elem_size, bool aligned16) {
 }
 
 int launch_energy_tc(const EnergyParams& p, const TcPlan& plan, cudaStream_t stream) {
-    if (p.mode == kModeBwd) return DDDM_ERR_UNSUPPORTED;
+    if (p.mode == kModeBwd && (p.x0_f32 || p.dist == nullptr || p.grad_xhat == nullptr)) return DDDM_ERR_UNSUPPORTED;
     CUtensorMap map, map_g;
     if (umma::make_tensor_map_bf16_rows(&map, p.xhat, (uint64_t)p.B * p.m, (uint64_t)p.D, (uint32_t)p.m)) return DDDM_ERR_UNSUPPORTED;
     // the gradient leaves through TMA tensor stores of [m draws x 128 columns] tiles (a forward-only launch never stores)

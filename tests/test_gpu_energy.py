@@ -387,6 +387,15 @@ def test_tensor_core_kernel(dev, m):
                 d = dist.cpu().numpy().astype(np.float64)
                 ok = np.abs(d - d_ref) <= 2e-3 * d_ref + 1e-12
                 assert ok.all(), (m, B, D, regime, float(np.max(np.abs(d - d_ref) / np.maximum(d_ref, 1e-30))))
+                # split backward on the same kernel (distances from `dist`, two upstream gradients, grad_x0 = -sum_i grad_i)
+                gc, gi = torch.tensor([0.37], device=dev), torch.tensor([-1.9], device=dev)
+                gx, gx0 = ops.energy_terms_bwd(xh, c, dist, gc, gi, beta, True)
+                ref_gx, ref_gx0 = oracle.energy_terms_grad(xh64, x064, beta, 0.37, -1.9, want_x0=True)
+                gscale = max(np.max(np.abs(ref_gx)), np.max(np.abs(ref_gx0)), 1e-6)
+                assert np.max(np.abs(gx.float().cpu().numpy() - ref_gx)) <= BF16_REL * gscale, (m, B, D, regime, "bwd grad_xhat")
+                assert np.max(np.abs(gx0.float().cpu().numpy() - ref_gx0)) <= BF16_REL * gscale, (m, B, D, regime, "bwd grad_x0")
+                gx_only, none = ops.energy_terms_bwd(xh, c, dist, gc, gi, beta, False)
+                assert torch.equal(gx_only, gx)
     finally:
         _cabi.set_tuning("energy.variant", 0)
 

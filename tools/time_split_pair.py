@@ -12,9 +12,11 @@ from ddm_b200 import _cabi
 ap = argparse.ArgumentParser()
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--streams", type=int, default=4)
+ap.add_argument("--m", type=int, default=8)
 a = ap.parse_args()
 L = _cabi.lib()
-B, m, D = 128, 8, 3072
+ap2 = None
+B, m, D = 128, a.m, 3072
 dev = torch.device("cuda:0")
 td = torch.float32 if a.dtype == "f32" else torch.bfloat16
 esz = 4 if a.dtype == "f32" else 2
