@@ -243,6 +243,15 @@ static int energy_terms_bwd(const T* xhat, const T* x0, const float* dist, const
         }
         if (tuning().variant == 3) return DDDM_ERR_UNSUPPORTED;
     }
+    if (tuning().variant == 0 || tuning().variant == 4) {
+        // blocked packed-fp32 kernel (m = 16, 24, 32) in backward mode: pass 2 only, coefficients from the saved distances
+        SmemPlan bp = plan_blk(m, D, (int)sizeof(T), al);
+        if (bp.ok) {
+            p.mode = kModeBwd;
+            return launch_energy_blk<T>(p, bp, stream);
+        }
+        if (tuning().variant == 4) return DDDM_ERR_UNSUPPORTED;
+    }
     if (tuning().variant != 2) {
         RegPlan plan = plan_reg(m, D, (int)sizeof(T), al, true);
         if (plan.ok) return launch_energy_bwd_reg<T>(p, plan, stream);

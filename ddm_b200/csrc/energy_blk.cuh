@@ -67,7 +67,11 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x >> 5) - 1;
     const int nthr = nwarps * 32;
     const bool control = warp == nwarps;
-    const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    // kModeBwd (the backward of the split pair): distances come from the forward's `dist`, so there is no pass 1 and no
+    // cross-CTA sum — the D-slabs of a row run as independent CTAs (launched without a cluster, cluster_size == 1 here,
+    // slab index = blockIdx.x) — and grad_x0 = - sum_i grad_xhat_i falls out of pass 2 (the pair terms cancel in the sum).
+    const bool bwd = p.mode == kModeBwd;
+    const int rank = (cluster_size > 1) ? (int)cg::this_cluster().block_rank() : (bwd ? (int)blockIdx.x : 0);
     const int b = blockIdx.y;
     if (cluster_size > 1) cluster_arrive_relaxed();
 
@@ -104,7 +108,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     __syncwarp();
     const float W = (p.mode == kModeLoss) ? p.weight_dev[0] * p.weight_scale : 1.0f;
     cudaTriggerProgrammaticLaunchCompletion();
-    if (control) {
+    if (control && !bwd) {
         // the otherwise idle control warp owns the M confinement distances ||x_i - x0||^2 (slots 0..M-1 of table 0)
         const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
         float2 acc2[M];
@@ -129,8 +133,9 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
         WarpReduce<M>::run(acc, s_warp, lane);  // conf slot i == table-0 entry i
     }
     const float nb = (float)p.B * (float)M;
-    const float pre_conf = 2.0f * W / nb;
-    const float pre_pair = -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
+    const float pre_conf = bwd ? 2.0f * p.g_conf[0] / nb : 2.0f * W / nb;
+    const float pre_pair = bwd ? 4.0f * p.g_inter[0] / (nb * (float)(M - 1))
+                               : -4.0f * W * (p.lam / (2.0f * (float)(M - 1))) / (nb * (float)(M - 1));
 
     // ---- pass 1: block sweeps.  A work unit = (sweep, column split); units are dealt to the warps round-robin, the
     //      warp's lanes stride the unit's columns, so every distance of a split is produced by exactly one warp. ----
@@ -248,7 +253,13 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
         // pass 2 reads every chunk: make sure this thread has observed all of them
         while (waited < nchunks - 1) mbar_wait(&s_bar[++waited], 0);
     };
-    if (!control) sweeps(std::true_type{});
+    if (!control) {
+        if (!bwd) {
+            sweeps(std::true_type{});
+        } else {
+            for (int c = 0; c < nchunks; ++c) mbar_wait(&s_bar[c], 0);  // pass 2 reads every chunk
+        }
+    }
     __syncthreads();
 
     // ---- sum over column splits and over the cluster (fixed order).  Cross-CTA: every CTA folds its splits into
@@ -257,6 +268,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     cg::cluster_group cluster = cg::this_cluster();
     auto table_sum = [&](int s) {
         float total = 0.f;
+        if (bwd) return p.dist[(long)b * P + s];
         if (cluster_size > 1) {
             for (int r = 0; r < cluster_size; ++r) total += cluster.map_shared_rank(s_warp, r)[s];
         } else {
@@ -295,20 +307,20 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
             } else {
                 s_K[idx] = pre_pair * der;
             }
-            if (p.dist != nullptr && rank == 0) p.dist[(long)b * P + s] = total;
+            if (p.dist != nullptr && rank == 0 && !bwd) p.dist[(long)b * P + s] = total;
         }
         if (cluster_size > 1) cluster_arrive_release();  // I no longer read my peers' tables
         __syncthreads();
     };
-    exchange_and_coefs(true, true);
-    const bool redo = s_close != 0;  // CTA- and cluster-uniform
-    if (redo) {
+    exchange_and_coefs(!bwd, true);
+    const bool redo = s_close != 0;  // CTA- and cluster-uniform (backward-only: the verdict alone, nothing to redo)
+    if (redo && !bwd) {
         if (cluster_size > 1) cluster_wait_acquire();  // every peer is done with my table before it is rewritten
         __syncthreads();
         if (!control) sweeps(std::false_type{});
         __syncthreads();
         exchange_and_coefs(false, false);
-    } else if (tid < M) {  // centred pass 2: diagonal of the coefficient matrix
+    } else if (!redo && tid < M) {  // centred pass 2: diagonal of the coefficient matrix
         float a = s_A[tid];
         for (int j = 0; j < M; ++j)
             if (j != tid) a += s_K[(j > tid ? tid : j) * M + (j > tid ? j : tid)];
@@ -318,7 +330,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
 
     if (control) {
         if (cluster_size > 1) cluster_wait_acquire();  // nobody's shared memory goes away while a peer may read it
-        if (rank == 0) {
+        if (rank == 0 && !bwd) {
             float c = 0.f, it = 0.f;
             for (int s = lane; s < P; s += 32) {
                 const float v = s_val[s];
@@ -334,6 +346,7 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
     // ---- pass 2: column owner ----
     if (p.grad_xhat != nullptr && nq > 0) {
         T* __restrict__ grow = static_cast<T*>(p.grad_xhat) + (long)b * M * p.D + v_begin * VEC;
+        T* __restrict__ g0row = (bwd && p.grad_x0 != nullptr) ? static_cast<T*>(p.grad_x0) + (long)b * p.D + v_begin * VEC : nullptr;
         const unsigned char* x0row = s_tile + (size_t)M * row_bytes;
         if (!redo) {
             // centred: g_i = (c_i + sum_j k_ij) z_i - sum_j k_ij z_j — one FMA per ordered pair
@@ -370,6 +383,13 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
                 }
 #pragma unroll
                 for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+                if (g0row != nullptr) {  // d/dx0 = - sum_i d/dxhat_i (fixed order)
+                    float2 s0 = g[0][0];
+#pragma unroll
+                    for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][0]);
+                    float2 neg[1] = {make_float2(-s0.x, -s0.y)};
+                    stg_step<T, COLS>(g0row + (long)q * COLS, neg);
+                }
             }
             return;
         }
@@ -403,6 +423,13 @@ energy_fused_blk_kernel(const EnergyParams p, const int slab_vecs, const int clu
             }
 #pragma unroll
             for (int i = 0; i < M; ++i) stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+            if (g0row != nullptr) {
+                float2 s0 = g[0][0];
+#pragma unroll
+                for (int i = 1; i < M; ++i) s0 = __fadd2_rn(s0, g[i][0]);
+                float2 neg[1] = {make_float2(-s0.x, -s0.y)};
+                stg_step<T, COLS>(g0row + (long)q * COLS, neg);
+            }
         }
     }
 }

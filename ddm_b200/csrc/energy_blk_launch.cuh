@@ -12,8 +12,10 @@ int launch_energy_blk_m(const EnergyParams& p, const SmemPlan& plan, cudaStream_
     auto kernel = two ? energy_fused_blk_kernel<T, M, 2> : energy_fused_blk_kernel<T, M, 1>;
     static SmemOptIn configured[2];  // per instantiation and per device
     if (int e = configured[two ? 1 : 0].ensure(kernel, plan.smem_bytes, 40 * 1024)) return e;
-    return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, plan.cluster, stream,
-                             p, plan.slab_vecs, plan.cluster, plan.chunk_vecs);
+    // the backward needs no cross-CTA sum: same grid, but the D-slabs of a row run as independent CTAs
+    const int cluster = (p.mode == kModeBwd) ? 1 : plan.cluster;
+    return launch_with_attrs(kernel, dim3(plan.cluster, p.B), dim3(plan.threads + 32), plan.smem_bytes, cluster, stream,
+                             p, plan.slab_vecs, cluster, plan.chunk_vecs);
 }
 
 template <typename T>

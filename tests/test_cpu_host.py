@@ -210,7 +210,7 @@ def test_sass_shows_tma_bulk_copies_packed_fp32_and_tcgen05():
     smem = [k for k in per_kernel if "energy_fused_smem_kernelIfLi8" in k.split("\n", 1)[0]]
     blk = [k for k in per_kernel if "energy_fused_blk_kernelIfLi32" in k.split("\n", 1)[0]]
     assert smem and blk
-    ldgsts = [k for k in smem if "ELb0ELi1ELb0EEEv" in k.split("\n", 1)[0]]  # the cp.async loader instantiation
+    ldgsts = [k for k in smem if "ELb0ELi1ELb0ELi4EEEv" in k.split("\n", 1)[0]]  # the cp.async loader instantiation (LOADER = 1)
     assert ldgsts and len(ldgsts) < len(smem)
     for k in ldgsts:
         assert "LDGSTS" in k and "LDGDEPBAR" in k, "cp.async loader: LDGSTS + commit groups expected"
