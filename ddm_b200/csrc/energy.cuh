@@ -32,6 +32,8 @@ struct EnergyParams {
     int x0_f32;                 // bf16 kernels: x0 is fp32 (mixed entry point; TMA-staged kernel only)
     int window;                 // cp.async loader of the TMA-staged kernel: column chunks in flight per CTA
     int ld_hint, st_hint;       // L2 eviction priority of the streaming loads / stores (single-wave kernel; 0 = normal)
+    int bulk_store;             // TMA-staged kernel: gradient rows leave through shared -> global bulk copies (1) or 16-byte stores (0)
+    int finish;                 // TMA-staged kernel: cross-row sum by the arrival ticket (1) or by polled row slots (0 / 2)
     unsigned long long* trace;  // diagnostics: 8 globaltimer stamps per CTA, or null (dddm_set_trace_buffer)
 };
 
@@ -160,6 +162,72 @@ __device__ __forceinline__ void finish_row(const EnergyParams& p, int b, float c
             p.out[1] = inter;
         }
         *p.ticket = 0u;  // leave the workspace reusable
+    }
+}
+
+// The same cross-row sum without a ticket (kernels with exactly one publishing CTA per row, all rows of the launch
+// resident or at least schedulable while one CTA waits: the TMA-staged kernel).  The ticket protocol costs the LAST row
+// three dependent round trips to L2 (exchange, increment, reads of the other rows) while L2 is busy with pass 2's
+// stores — ~1 us each, and the launch ends with them.  Here a row's sums ARE its flag: one 8-byte store with bit 63
+// set (both sums are non-negative, their sign bits are free); the control warp of the launch's last row (b = B - 1)
+// polls the B slots, adds them in the same fixed order as finish_row (bit-identical result), and clears them, so the
+// workspace stays usable by either protocol: the ticket protocol leaves bit 63 clear (= "not arrived" here), this one
+// leaves zeros.  Critical path of the last row: one store + one load round trip.
+__device__ __forceinline__ void finish_row_polled(const EnergyParams& p, int b, float conf_row, float inter_row, float W,
+                                                  int lane) {
+    unsigned long long* slots = reinterpret_cast<unsigned long long*>(p.row_partials);
+    if (lane == 0) {
+        const unsigned long long packed = (unsigned long long)(__float_as_uint(conf_row) & 0x7fffffffu) |
+                                          ((unsigned long long)(__float_as_uint(inter_row) | 0x80000000u) << 32);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slots + b), "l"(packed) : "memory");
+    }
+    if (b != p.B - 1) return;
+    float c = 0.f, i = 0.f;
+    for (int r0 = 0; r0 < p.B; r0 += 128) {
+        unsigned long long v[4];
+        bool all;
+        unsigned spins = 0;
+        do {
+            all = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 32 + lane;
+                v[u] = 1ull << 63;
+                if (r < p.B) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[u]) : "l"(slots + r) : "memory");
+                all = all && (v[u] >> 63);
+            }
+            // A row that never arrives means the workspace is shared with a concurrent launch (a contract violation:
+            // one workspace per stream) or an earlier launch was aborted: after ~1 s give up with NaN sums, never hang.
+            if (!all && ++spins > (1u << 20)) {
+                c = __int_as_float(0x7fc00000);
+                break;
+            }
+        } while (!all);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 32 + lane;
+            if (r < p.B) {
+                c += __uint_as_float((unsigned)v[u]);
+                i += __uint_as_float((unsigned)(v[u] >> 32) & 0x7fffffffu);
+                slots[r] = 0ull;
+            }
+        }
+    }
+    c = warp_sum(c);
+    i = warp_sum(i);
+    if (lane == 0) {
+        const float conf = c / ((float)p.B * (float)p.m);
+        const float inter = i / ((float)p.B * (float)p.m * (float)(p.m - 1));
+        if (p.mode == kModeLoss) {
+            const float cl = p.lam / (2.0f * (float)(p.m - 1));
+            p.out[0] = W * (conf - cl * inter);
+            p.out[1] = conf;
+            p.out[2] = inter;
+            p.out[3] = W;
+        } else {
+            p.out[0] = conf;
+            p.out[1] = inter;
+        }
     }
 }
 

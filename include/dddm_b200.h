@@ -55,8 +55,10 @@ const char* dddm_strerror(int status);
 /* ------------------------------------------------------------------------------------------
  * Energy-score workspace.  `workspace` passed to the energy kernels must hold
  * dddm_energy_workspace_bytes(B, m) bytes, 16-byte aligned, and must be ZERO-INITIALISED once
- * before first use; the kernels leave it reusable (the arrival ticket is reset by the last CTA).
- * One workspace must not be shared by launches that may run concurrently.
+ * before first use; the kernels leave it reusable (the arrival ticket is reset by the last CTA, the
+ * polled row slots of the TMA-staged kernel are cleared by the CTA that sums them).
+ * One workspace must not be shared by launches that may run concurrently (one workspace per stream):
+ * their row sums would mix; the TMA-staged kernel then reports NaN sums after a bounded wait.
  * ------------------------------------------------------------------------------------------ */
 size_t dddm_energy_workspace_bytes(int B, int m);
 /* number of floats per row in the saved-distance buffer of the split fwd/bwd pair: m + m(m-1)/2 */

@@ -25,6 +25,9 @@ def time_config(L, B, m, D, dtype, iters=2400, two_streams=False, nstreams=1, ns
     dev = torch.device("cuda:0")
     algo = (2 * B * m * D + B * D) * esz
     nsets = nsets_override or max(4, -(-2 * 126 * 2**20 // algo) + 1)
+    if two_streams:
+        nstreams = 2
+    nsets = -(-nsets // nstreams) * nstreams  # set i always runs on stream i % nstreams: one workspace, one stream
     fn = getattr(L, f"dddm_energy_fused_{dtype}")
     sets = []
     for s in range(nsets):
@@ -103,7 +106,7 @@ def main():
         configs = [dict(variant=3, cluster=c, threads=t, pdl=1) for c, t in
                    itertools.product((1, 2, 4, 8), (32, 64, 96, 128, 192, 256))]
     for cfg in configs:
-        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols", "ksmem", "loader", "window", "ldhint", "sthint", "nostore"):
+        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols", "ksmem", "loader", "window", "ldhint", "sthint", "nostore", "finish", "bulkst"):
             _cabi.set_tuning(f"energy.{k}", int(cfg.get(k, 1 if k == "pdl" else 0)))
         desc = _cabi.describe_energy(a.B, a.m, a.D, a.dtype)
         try:
