@@ -107,7 +107,7 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     p.ld_hint = tuning().ldhint;
     p.st_hint = tuning().sthint;
     p.finish = tuning().finish;
-    p.bulk_store = tuning().bulkst == 2;
+    p.bulk_store = tuning().bulkst == 2 ? 1 : tuning().bulkst == 3 ? 2 : 0;  // TMA-staged kernel, pass 2: 1 bulk stores, 2 wide stores
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
     // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel

@@ -90,6 +90,26 @@ __device__ __forceinline__ void sts_step(unsigned char* row, int q, const float2
         reinterpret_cast<uint32_t*>(row)[q] = pack_bf16x2(g[0].x, g[0].y);
     }
 }
+// Two adjacent steps (this lane's and its pair lane's) of one row in ONE store of twice the width: 32 bytes per lane
+// (STG.256, new in sm_100) for fp32 steps of 4 columns, 16 bytes for bf16.  `dst` is aligned to the doubled width.
+template <typename T, int COLS>
+__device__ __forceinline__ void stg_step_wide(T* __restrict__ dst, const float2 (&lo)[COLS / 2], const float2 (&hi)[COLS / 2]) {
+    if constexpr (sizeof(T) == 4 && COLS == 4) {
+        asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(lo[0].x), "f"(lo[0].y),
+                     "f"(lo[1].x), "f"(lo[1].y), "f"(hi[0].x), "f"(hi[0].y), "f"(hi[1].x), "f"(hi[1].y)
+                     : "memory");
+    } else if constexpr (sizeof(T) == 4) {
+        uint4 r;
+        r.x = __float_as_uint(lo[0].x); r.y = __float_as_uint(lo[0].y);
+        r.z = __float_as_uint(hi[0].x); r.w = __float_as_uint(hi[0].y);
+        stg_stream16(dst, r);
+    } else if constexpr (COLS == 4) {
+        stg_stream16(dst, make_uint4(pack_bf16x2(lo[0].x, lo[0].y), pack_bf16x2(lo[1].x, lo[1].y),
+                                     pack_bf16x2(hi[0].x, hi[0].y), pack_bf16x2(hi[1].x, hi[1].y)));
+    } else {
+        stg_stream8(dst, make_uint2(pack_bf16x2(lo[0].x, lo[0].y), pack_bf16x2(hi[0].x, hi[0].y)));
+    }
+}
 // shared -> global bulk copy (TMA store, 1-D), tracked in the issuing thread's bulk async-group
 __device__ __forceinline__ void tma_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
@@ -475,7 +495,47 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
                         }
                 }
             };
-            if (LOADER == 0 && p.bulk_store != 0) {
+            if (p.bulk_store == 2 && ((reinterpret_cast<uintptr_t>(grow) | ((size_t)p.D * sizeof(T))) & (2 * SB - 1)) == 0) {
+                // Wide stores: an SM's store path retires about one warp-level store INSTRUCTION per 21 cycles whatever its
+                // width (tools/ubench/store_width.cu; pass 2 takes 2.1 us in fp32 and in bf16), so the two lanes of a pair
+                // trade halves (row i goes to the even lane, row i + 1 to the odd one) and every lane issues M / 2 stores of
+                // twice the width — STG.256 for fp32.  Warp-uniform trip count (the shuffles need every lane).
+                const bool odd = (lane & 1) != 0;
+                for (int q0 = warp * 32; q0 < nq; q0 += nthr) {
+                    const int q = q0 + lane;
+                    const bool valid = q < nq, pair_ok = (q | 1) < nq;
+                    float2 g[M][NP];
+                    if (valid) {
+                        centred_step(q, g);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < M; ++i)
+#pragma unroll
+                            for (int h = 0; h < NP; ++h) g[i][h] = make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i + 1 < M; i += 2) {
+                        float2 recv[NP];
+#pragma unroll
+                        for (int h = 0; h < NP; ++h) {
+                            const float2 send = odd ? g[i][h] : g[i + 1][h];
+                            recv[h].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                            recv[h].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                        }
+                        if (pair_ok) {
+                            T* dst = grow + (long)(i + (odd ? 1 : 0)) * p.D + (long)(q & ~1) * COLS;
+                            if (odd) stg_step_wide<T, COLS>(dst, recv, g[i + 1]); else stg_step_wide<T, COLS>(dst, g[i], recv);
+                        } else if (valid) {  // an odd number of steps: the last one has no partner
+                            stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
+                            stg_step<T, COLS>(grow + (long)(i + 1) * p.D + (long)q * COLS, g[i + 1]);
+                        }
+                    }
+                    if ((M & 1) && valid) stg_step<T, COLS>(grow + (long)(M - 1) * p.D + (long)q * COLS, g[M - 1]);
+                }
+                if (tid == 0) DDDM_TRACE(5);
+                return;
+            }
+            if (LOADER == 0 && p.bulk_store == 1) {
                 // Gradient out through the TMA: an SM retires ~46 B/ns of 16-byte stores but ~56 B/ns of bulk stores
                 // (tools/ubench/copy_sol.cu push), and pass 2 of one row per SM is bound by exactly that.  Each warp owns
                 // a contiguous range of steps; g_i overwrites x_i in the tile (the step's columns are read by this thread

@@ -468,7 +468,8 @@ def test_kernel_variants_agree(dev):
 
 def test_finish_protocols_and_bulk_store_pass2_bit_identical(dev):
     """TMA-staged kernel: the cross-row sum by polled row slots (default) and by the arrival ticket, and pass 2 through
-    bulk stores from the tile or 16-byte stores from registers, give bit-identical sums and gradients (same arithmetic,
+    bulk stores from the tile, 16-byte stores from registers or double-width stores by lane pairs (STG.256 for fp32),
+    give bit-identical sums and gradients (same arithmetic,
     same summation order) — on one workspace used alternately by both protocols, for more rows than one wave holds, ragged D,
     D-split clusters, fp32 / bf16 / mixed inputs."""
     from ddm_b200 import _cabi
@@ -477,13 +478,15 @@ def test_finish_protocols_and_bulk_store_pass2_bit_identical(dev):
         for B, m, D, cluster, dtype, x0f32 in ((128, 8, 3072, 0, torch.float32, False), (700, 8, 3072, 0, torch.float32, False),
                                                (5, 7, 1000, 0, torch.float32, False), (33, 8, 3072 - 40, 2, torch.float32, False),
                                                (128, 8, 3072, 0, torch.bfloat16, False), (128, 8, 3072, 0, torch.bfloat16, True),
-                                               (9, 5, 264, 4, torch.bfloat16, False), (1, 2, 8, 0, torch.float32, False)):
+                                               (9, 5, 264, 4, torch.bfloat16, False), (1, 2, 8, 0, torch.float32, False),
+                                               (3, 8, 12, 0, torch.float32, False), (4, 3, 3076, 0, torch.float32, False),
+                                               (6, 6, 520, 0, torch.bfloat16, False)):
             xh, x0 = _synthetic(B, m, D, "late", seed=B + D)
             xh, x0 = xh.to(dev).to(dtype), x0.to(dev).to(torch.float32 if x0f32 else dtype)
             _cabi.set_tuning("energy.variant", 3)
             _cabi.set_tuning("energy.cluster", cluster)
             ref_out = ref_g = None
-            for finish, bulk in ((1, 1), (2, 1), (1, 2), (2, 2), (0, 0), (1, 1), (2, 2)):
+            for finish, bulk in ((1, 1), (2, 1), (1, 2), (2, 2), (0, 0), (1, 3), (2, 3), (1, 1), (2, 2)):
                 _cabi.set_tuning("energy.finish", finish)
                 _cabi.set_tuning("energy.bulkst", bulk)
                 out, g = _fused(xh, x0, 0.7, 0.1, 1.3)
