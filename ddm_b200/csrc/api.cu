@@ -107,7 +107,6 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
     p.ld_hint = tuning().ldhint;
     p.st_hint = tuning().sthint;
     p.finish = tuning().finish;
-    p.bulk_store = tuning().bulkst == 2 ? 1 : tuning().bulkst == 3 ? 2 : 0;  // TMA-staged kernel, pass 2: 1 bulk stores, 2 wide stores
     const bool al = is_aligned16(p.xhat) && is_aligned16(p.x0) && (!p.grad_xhat || is_aligned16(p.grad_xhat)) &&
                     ((long)p.D * (long)sizeof(T)) % 16 == 0;
     // kernel selection: TMA-staged packed-fp32 kernel (m <= 8, aligned rows) > register-resident kernel
@@ -364,7 +363,6 @@ int dddm_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "energy.sthint")) t.sthint = value;
     else if (!strcmp(key, "energy.nostore")) t.nostore = value;
     else if (!strcmp(key, "energy.finish")) t.finish = value;
-    else if (!strcmp(key, "energy.bulkst")) t.bulkst = value;
     else if (!strcmp(key, "nvtx")) t.nvtx = value ? 1 : 0;
     else return DDDM_ERR_BAD_ARGUMENT;
     return DDDM_OK;
@@ -385,7 +383,6 @@ int dddm_get_tuning(const char* key) {
     if (!strcmp(key, "energy.ldhint")) return t.ldhint;
     if (!strcmp(key, "energy.sthint")) return t.sthint;
     if (!strcmp(key, "energy.finish")) return t.finish;
-    if (!strcmp(key, "energy.bulkst")) return t.bulkst;
     if (!strcmp(key, "energy.nostore")) return t.nostore;
     if (!strcmp(key, "nvtx")) return t.nvtx;
     return DDDM_ERR_BAD_ARGUMENT;

@@ -31,8 +31,6 @@ struct Tuning {
     int sthint = 0;   // ... and of the gradient stores
     int nostore = 0;  // diagnostics: pass 2 without its global stores (fp32/bf16 m = 8, 256 x 3 plan only)
     int ctas = 0;     // experiment: resident-CTA target the bf16 variant-3 kernel is compiled for (0 = default)
-    int bulkst = 0;   // TMA-staged kernel, pass 2: 0 auto, 1 16-byte stores from registers, 2 bulk stores from the tile,
-                      // 3 lane pairs trade halves and store twice the width (STG.256 for fp32)
     int finish = 0;   // TMA-staged kernel: cross-row sum 0 auto (polled row slots), 1 arrival ticket, 2 polled row slots
     int nvtx = -1;    // NVTX ranges around the C-ABI entry points: -1 = environment DDDM_NVTX, 0 off, 1 on
     void* trace = nullptr;  // device buffer for in-kernel timeline stamps (diagnostics)

@@ -32,7 +32,6 @@ struct EnergyParams {
     int x0_f32;                 // bf16 kernels: x0 is fp32 (mixed entry point; TMA-staged kernel only)
     int window;                 // cp.async loader of the TMA-staged kernel: column chunks in flight per CTA
     int ld_hint, st_hint;       // L2 eviction priority of the streaming loads / stores (single-wave kernel; 0 = normal)
-    int bulk_store;             // TMA-staged kernel, pass 2: 0 one store per step, 1 shared -> global bulk copies, 2 wide stores by lane pairs
     int finish;                 // TMA-staged kernel: cross-row sum by the arrival ticket (1) or by polled row slots (0 / 2)
     unsigned long long* trace;  // diagnostics: 8 globaltimer stamps per CTA, or null (dddm_set_trace_buffer)
 };

@@ -77,45 +77,6 @@ __device__ __forceinline__ void stg_step(T* __restrict__ dst, const float2 (&g)[
     }
 }
 
-// the same step written back into the shared-memory tile (pass 2 with bulk stores: g_i takes the place of x_i)
-template <typename T, int COLS>
-__device__ __forceinline__ void sts_step(unsigned char* row, int q, const float2 (&g)[COLS / 2]) {
-    if constexpr (sizeof(T) == 4 && COLS == 4) {
-        reinterpret_cast<float4*>(row)[q] = make_float4(g[0].x, g[0].y, g[1].x, g[1].y);
-    } else if constexpr (sizeof(T) == 4) {
-        reinterpret_cast<float2*>(row)[q] = g[0];
-    } else if constexpr (COLS == 4) {
-        reinterpret_cast<uint2*>(row)[q] = make_uint2(pack_bf16x2(g[0].x, g[0].y), pack_bf16x2(g[1].x, g[1].y));
-    } else {
-        reinterpret_cast<uint32_t*>(row)[q] = pack_bf16x2(g[0].x, g[0].y);
-    }
-}
-// Two adjacent steps (this lane's and its pair lane's) of one row in ONE store of twice the width: 32 bytes per lane
-// (STG.256, new in sm_100) for fp32 steps of 4 columns, 16 bytes for bf16.  `dst` is aligned to the doubled width.
-template <typename T, int COLS>
-__device__ __forceinline__ void stg_step_wide(T* __restrict__ dst, const float2 (&lo)[COLS / 2], const float2 (&hi)[COLS / 2]) {
-    if constexpr (sizeof(T) == 4 && COLS == 4) {
-        asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(lo[0].x), "f"(lo[0].y),
-                     "f"(lo[1].x), "f"(lo[1].y), "f"(hi[0].x), "f"(hi[0].y), "f"(hi[1].x), "f"(hi[1].y)
-                     : "memory");
-    } else if constexpr (sizeof(T) == 4) {
-        uint4 r;
-        r.x = __float_as_uint(lo[0].x); r.y = __float_as_uint(lo[0].y);
-        r.z = __float_as_uint(hi[0].x); r.w = __float_as_uint(hi[0].y);
-        stg_stream16(dst, r);
-    } else if constexpr (COLS == 4) {
-        stg_stream16(dst, make_uint4(pack_bf16x2(lo[0].x, lo[0].y), pack_bf16x2(lo[1].x, lo[1].y),
-                                     pack_bf16x2(hi[0].x, hi[0].y), pack_bf16x2(hi[1].x, hi[1].y)));
-    } else {
-        stg_stream8(dst, make_uint2(pack_bf16x2(lo[0].x, lo[0].y), pack_bf16x2(hi[0].x, hi[0].y)));
-    }
-}
-// shared -> global bulk copy (TMA store, 1-D), tracked in the issuing thread's bulk async-group
-__device__ __forceinline__ void tma_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-}
-
 template <int M>
 __host__ __device__ constexpr int pair_slot(int i, int j) {  // i < j
     return M + i * M - i * (i + 1) / 2 + (j - i - 1);
@@ -471,97 +432,6 @@ energy_fused_smem_kernel(const EnergyParams p, const int slab_vecs, const int cl
                 for (int j = 0; j < M; ++j)
                     if (j != i) a += K2[pair_slot<M>(i < j ? i : j, i < j ? j : i)].x;
                 K2[i] = make_float2(a, a);
-            }
-            auto centred_step = [&](int q, float2 (&g)[M][NP]) {
-                float2 x[M + 1][NP];
-#pragma unroll
-                for (int r = 0; r < M; ++r) lds_step<T, COLS>(s_tile + (size_t)r * row_bytes, q, x[r]);
-                lds_step<T0, COLS>(s_tile + (size_t)M * row_bytes, q, x[M]);
-#pragma unroll
-                for (int h = 0; h < NP; ++h) {
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        x[i][h] = sub2(x[i][h], x[M][h]);  // z_i
-                        g[i][h] = __fmul2_rn(K2[i], x[i][h]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < M; ++i)
-#pragma unroll
-                        for (int j = i + 1; j < M; ++j) {
-                            const float2 k = K2[pair_slot<M>(i, j)];
-                            const float2 nk = make_float2(-k.x, -k.y);  // folded into FFMA2's operand modifier
-                            g[i][h] = __ffma2_rn(nk, x[j][h], g[i][h]);
-                            g[j][h] = __ffma2_rn(nk, x[i][h], g[j][h]);
-                        }
-                }
-            };
-            if (p.bulk_store == 2 && ((reinterpret_cast<uintptr_t>(grow) | ((size_t)p.D * sizeof(T))) & (2 * SB - 1)) == 0) {
-                // Wide stores: an SM's store path retires about one warp-level store INSTRUCTION per 21 cycles whatever its
-                // width (tools/ubench/store_width.cu; pass 2 takes 2.1 us in fp32 and in bf16), so the two lanes of a pair
-                // trade halves (row i goes to the even lane, row i + 1 to the odd one) and every lane issues M / 2 stores of
-                // twice the width — STG.256 for fp32.  Warp-uniform trip count (the shuffles need every lane).
-                const bool odd = (lane & 1) != 0;
-                for (int q0 = warp * 32; q0 < nq; q0 += nthr) {
-                    const int q = q0 + lane;
-                    const bool valid = q < nq, pair_ok = (q | 1) < nq;
-                    float2 g[M][NP];
-                    if (valid) {
-                        centred_step(q, g);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < M; ++i)
-#pragma unroll
-                            for (int h = 0; h < NP; ++h) g[i][h] = make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int i = 0; i + 1 < M; i += 2) {
-                        float2 recv[NP];
-#pragma unroll
-                        for (int h = 0; h < NP; ++h) {
-                            const float2 send = odd ? g[i][h] : g[i + 1][h];
-                            recv[h].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
-                            recv[h].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
-                        }
-                        if (pair_ok) {
-                            T* dst = grow + (long)(i + (odd ? 1 : 0)) * p.D + (long)(q & ~1) * COLS;
-                            if (odd) stg_step_wide<T, COLS>(dst, recv, g[i + 1]); else stg_step_wide<T, COLS>(dst, g[i], recv);
-                        } else if (valid) {  // an odd number of steps: the last one has no partner
-                            stg_step<T, COLS>(grow + (long)i * p.D + (long)q * COLS, g[i]);
-                            stg_step<T, COLS>(grow + (long)(i + 1) * p.D + (long)q * COLS, g[i + 1]);
-                        }
-                    }
-                    if ((M & 1) && valid) stg_step<T, COLS>(grow + (long)(M - 1) * p.D + (long)q * COLS, g[M - 1]);
-                }
-                if (tid == 0) DDDM_TRACE(5);
-                return;
-            }
-            if (LOADER == 0 && p.bulk_store == 1) {
-                // Gradient out through the TMA: an SM retires ~46 B/ns of 16-byte stores but ~56 B/ns of bulk stores
-                // (tools/ubench/copy_sol.cu push), and pass 2 of one row per SM is bound by exactly that.  Each warp owns
-                // a contiguous range of steps; g_i overwrites x_i in the tile (the step's columns are read by this thread
-                // only), and after every kBlk warp-iterations (~1 KB per row) lanes 0..M-1 send one row segment each.
-                constexpr int kBlk = (1024 / (32 * SB)) > 0 ? 1024 / (32 * SB) : 1;
-                const int per_warp = (nq + nthr - 1) / nthr * 32;  // steps per warp, a multiple of 32
-                const int w_begin = min(nq, warp * per_warp), w_end = min(nq, (warp + 1) * per_warp);
-                for (int q0 = w_begin; q0 < w_end; q0 += 32 * kBlk) {
-                    const int q1 = min(w_end, q0 + 32 * kBlk);
-                    for (int q = q0 + lane; q < q1; q += 32) {
-                        float2 g[M][NP];
-                        centred_step(q, g);
-#pragma unroll
-                        for (int i = 0; i < M; ++i) sts_step<T, COLS>(s_tile + (size_t)i * row_bytes, q, g[i]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my writes, visible to the async proxy
-                    __syncwarp();
-                    if (lane < M) {
-                        tma_bulk_s2g(reinterpret_cast<unsigned char*>(grow + (long)lane * p.D) + (size_t)q0 * SB,
-                                     s_tile + (size_t)lane * row_bytes + (size_t)q0 * SB, (uint32_t)(q1 - q0) * SB);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
-                if (lane < M) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile outlives its readers
-                if (tid == 0) DDDM_TRACE(5);
-                return;
             }
             for (int q = tid; q < nq; q += nthr) {
                 float2 x[M + 1][NP], g[M][NP];

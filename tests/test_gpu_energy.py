@@ -466,29 +466,24 @@ def test_kernel_variants_agree(dev):
     assert len(seen) >= 16, seen
 
 
-def test_finish_protocols_and_bulk_store_pass2_bit_identical(dev):
-    """TMA-staged kernel: the cross-row sum by polled row slots (default) and by the arrival ticket, and pass 2 through
-    bulk stores from the tile, 16-byte stores from registers or double-width stores by lane pairs (STG.256 for fp32),
-    give bit-identical sums and gradients (same arithmetic,
-    same summation order) — on one workspace used alternately by both protocols, for more rows than one wave holds, ragged D,
-    D-split clusters, fp32 / bf16 / mixed inputs."""
+def test_finish_protocols_bit_identical(dev):
+    """TMA-staged kernel: the cross-row sum by polled row slots (default) and by the arrival ticket give bit-identical
+    sums and gradients (same arithmetic, same summation order) — on one workspace used alternately by both protocols,
+    for more rows than one wave holds, ragged D, D-split clusters, fp32 / bf16 / mixed inputs."""
     from ddm_b200 import _cabi
 
     try:
         for B, m, D, cluster, dtype, x0f32 in ((128, 8, 3072, 0, torch.float32, False), (700, 8, 3072, 0, torch.float32, False),
                                                (5, 7, 1000, 0, torch.float32, False), (33, 8, 3072 - 40, 2, torch.float32, False),
                                                (128, 8, 3072, 0, torch.bfloat16, False), (128, 8, 3072, 0, torch.bfloat16, True),
-                                               (9, 5, 264, 4, torch.bfloat16, False), (1, 2, 8, 0, torch.float32, False),
-                                               (3, 8, 12, 0, torch.float32, False), (4, 3, 3076, 0, torch.float32, False),
-                                               (6, 6, 520, 0, torch.bfloat16, False)):
+                                               (9, 5, 264, 4, torch.bfloat16, False), (1, 2, 8, 0, torch.float32, False)):
             xh, x0 = _synthetic(B, m, D, "late", seed=B + D)
             xh, x0 = xh.to(dev).to(dtype), x0.to(dev).to(torch.float32 if x0f32 else dtype)
             _cabi.set_tuning("energy.variant", 3)
             _cabi.set_tuning("energy.cluster", cluster)
             ref_out = ref_g = None
-            for finish, bulk in ((1, 1), (2, 1), (1, 2), (2, 2), (0, 0), (1, 3), (2, 3), (1, 1), (2, 2)):
+            for finish in (1, 2, 0, 1, 1, 2, 2):
                 _cabi.set_tuning("energy.finish", finish)
-                _cabi.set_tuning("energy.bulkst", bulk)
                 out, g = _fused(xh, x0, 0.7, 0.1, 1.3)
                 assert np.all(np.isfinite(out))
                 if ref_out is None:
@@ -497,10 +492,10 @@ def test_finish_protocols_and_bulk_store_pass2_bit_identical(dev):
                     assert abs(out[1] - conf) <= FP32_REL * max(abs(conf), abs(inter))
                     assert _rel(g, grad) <= (FP32_REL if dtype == torch.float32 else BF16_REL)
                 else:
-                    assert np.array_equal(out, ref_out), (B, m, D, finish, bulk, out, ref_out)
-                    assert np.array_equal(g, ref_g), (B, m, D, finish, bulk)
+                    assert np.array_equal(out, ref_out), (B, m, D, finish, out, ref_out)
+                    assert np.array_equal(g, ref_g), (B, m, D, finish)
     finally:
-        for k in ("energy.variant", "energy.cluster", "energy.finish", "energy.bulkst"):
+        for k in ("energy.variant", "energy.cluster", "energy.finish"):
             _cabi.set_tuning(k, 0)
 
 

@@ -106,7 +106,7 @@ def main():
         configs = [dict(variant=3, cluster=c, threads=t, pdl=1) for c, t in
                    itertools.product((1, 2, 4, 8), (32, 64, 96, 128, 192, 256))]
     for cfg in configs:
-        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols", "ksmem", "loader", "window", "ldhint", "sthint", "nostore", "finish", "bulkst"):
+        for k in ("variant", "cluster", "nv", "pdl", "threads", "ctas", "cols", "ksmem", "loader", "window", "ldhint", "sthint", "nostore", "finish"):
             _cabi.set_tuning(f"energy.{k}", int(cfg.get(k, 1 if k == "pdl" else 0)))
         desc = _cabi.describe_energy(a.B, a.m, a.D, a.dtype)
         try:
