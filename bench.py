@@ -440,9 +440,10 @@ def run_aux(args, dev, world, rank, L, peak) -> dict:
         ref_ms, ref_v = timed(eager)
         aux["rbf_mmd2"] = {"n": n, "m": n, "D": D, "ms": ours_ms, "value": ours_v, "tf32_gram_ms": tf32_ms,
                            "tf32_gram_value": tf32_v, "eager_reference_formula_ms": ref_ms,
-                           "eager_value": ref_v, "note": "evaluation-side pairwise kernel (SURVEY 8f-4): fp32 GEMM tiles "
-                           "(cuBLAS; only the upper trapezoids of the symmetric xx/yy terms) + one fused "
-                           "distance/exp/mask/sum pass per tile"}
+                           "eager_value": ref_v, "note": "evaluation-side pairwise kernel (SURVEY 8f-4). ms: the default path at this size, ONE fused tcgen05 "
+                           "kernel per term (bf16 hi/lo split of the fp32 inputs, Gram tile in tensor memory, distance / exp / "
+                           "mask / sum epilogue, no n x n matrix in HBM; csrc/metrics_tc.cu). tf32_gram_ms: the library-GEMM tile "
+                           "path with allow_tf32=True, for comparison"}
     return aux
 
 

@@ -481,6 +481,7 @@ def test_finish_protocols_bit_identical(dev):
             xh, x0 = xh.to(dev).to(dtype), x0.to(dev).to(torch.float32 if x0f32 else dtype)
             _cabi.set_tuning("energy.variant", 3)
             _cabi.set_tuning("energy.cluster", cluster)
+            assert _cabi.describe_energy(B, m, D, "f32" if dtype == torch.float32 else "bf16").startswith("smem<")
             ref_out = ref_g = None
             for finish in (1, 2, 0, 1, 1, 2, 2):
                 _cabi.set_tuning("energy.finish", finish)
