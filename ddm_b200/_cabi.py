@@ -91,6 +91,7 @@ SIGNATURES = {
     "dddm_session_wait": (c_int, [c_void_p]),
     "dddm_session_packed_layout": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dddm_host_alloc": (c_void_p, [c_size_t]),
+    "dddm_host_alloc_input": (c_void_p, [c_size_t]),
     "dddm_host_free": (None, [c_void_p]),
     "dddm_last_error": (c_int, []),
     "dddm_set_tuning": (c_int, [c_char_p, c_int]),

@@ -213,6 +213,15 @@ void* dddm_host_alloc(size_t bytes) {
     }
     return p;
 }
+void* dddm_host_alloc_input(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined);
+    if (e != cudaSuccess) {
+        dddm::set_last_error((int)e);
+        return nullptr;
+    }
+    return p;
+}
 void dddm_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }

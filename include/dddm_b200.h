@@ -215,6 +215,9 @@ int dddm_session_wait(dddm_session*);
 int dddm_session_packed_layout(const dddm_session*, size_t* in_bytes, size_t* x0_offset, size_t* t_offset,
                                size_t* out_bytes, size_t* out_offset);
 void* dddm_host_alloc(size_t bytes); /* pinned host memory */
+/* Pinned, WRITE-COMBINED host memory for buffers the CPU only writes and the GPU only reads (a step's inputs):
+ * not snooped during the transfer; slow to read back on the CPU, so never use it for outputs.  Free with dddm_host_free. */
+void* dddm_host_alloc_input(size_t bytes);
 void dddm_host_free(void*);
 int dddm_last_error(void);
 

@@ -264,10 +264,11 @@ def test_host_session_matches_device_path(dev):
         finally:
             L.dddm_session_destroy(s)
     assert not L.dddm_session_create(0, 8, 4, 0, 0) and L.dddm_last_error() == -2
-    p = L.dddm_host_alloc(1024)
-    assert p
-    ctypes.memset(p, 0, 1024)
-    L.dddm_host_free(p)
+    for alloc in (L.dddm_host_alloc, L.dddm_host_alloc_input):  # pinned / pinned write-combined (inputs only)
+        p = alloc(1024)
+        assert p
+        ctypes.memset(p, 0, 1024)
+        L.dddm_host_free(p)
 
 
 def test_launch_counter(dev):

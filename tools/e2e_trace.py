@@ -127,6 +127,32 @@ def main() -> None:
         sess_run(n)
         dt = time.perf_counter() - t0
         print(f"C-ABI session, {n} steps: {1e3 * dt / n:.4f} ms/step ({B * n / dt:.0f} rows/s)")
+    # the same with WRITE-COMBINED pinned input buffers (dddm_host_alloc_input): the CPU only writes them
+    wc = []
+    for s in range(a.host_sets):
+        ptr = L.dddm_host_alloc_input(in_bytes)
+        assert ptr, "dddm_host_alloc_input failed"
+        ctypes.memmove(ptr, host[s][0].data_ptr(), in_bytes)
+        wc.append(ptr)
+
+    def sess_run_wc(n):
+        for i in range(n):
+            pin, pout = wc[i % a.host_sets], host[i % a.host_sets][1]
+            _cabi.check(L.dddm_session_enqueue_host(sess, pin, pin + x0_off, pin + t_off, 0.0, 0.1, 1.0, pout.data_ptr(),
+                                                    pout.data_ptr() + out_off))
+        _cabi.check(L.dddm_session_wait(sess))
+
+    ref_out = host[0][1][out_off:out_off + 16].clone()
+    sess_run_wc(8)
+    assert torch.equal(host[0][1][out_off:out_off + 16], ref_out), "write-combined inputs changed the result"
+    for n in (a.steps, a.steps, 10 * a.steps):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        sess_run_wc(n)
+        dt = time.perf_counter() - t0
+        print(f"C-ABI session, write-combined inputs, {n} steps: {1e3 * dt / n:.4f} ms/step ({B * n / dt:.0f} rows/s)")
+    for ptr in wc:
+        L.dddm_host_free(ptr)
     L.dddm_session_destroy(sess)
 
 
