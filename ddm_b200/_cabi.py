@@ -30,6 +30,7 @@ SIGNATURES = {
     "dddm_abi_version": (c_int, []),
     "dddm_strerror": (c_char_p, [c_int]),
     "dddm_energy_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "dddm_energy_workspace_reset": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dddm_energy_dist_per_row": (c_size_t, [c_int]),
     "dddm_energy_fused_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int,
                                       c_int, c_int, c_float, c_float, c_void_p]),

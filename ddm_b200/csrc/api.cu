@@ -291,6 +291,11 @@ size_t dddm_energy_workspace_bytes(int B, int m) {
     if (B < 1) B = 1;
     return sizeof(EnergyWorkspace) + (size_t)B * 2 * sizeof(float);
 }
+int dddm_energy_workspace_reset(void* workspace, int B, int m, dddm_stream_t stream) {
+    if (!workspace) return DDDM_ERR_NULL_POINTER;
+    if (B < 1) return DDDM_ERR_BAD_SHAPE;
+    return (int)cudaMemsetAsync(workspace, 0, dddm_energy_workspace_bytes(B, m), (cudaStream_t)stream);
+}
 size_t dddm_energy_dist_per_row(int m) { return m < 2 ? 0 : (size_t)m + (size_t)m * (m - 1) / 2; }
 
 int dddm_energy_fused_f32(const float* xhat, const float* x0, const float* weight_dev, float weight_scale,

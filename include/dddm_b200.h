@@ -61,6 +61,9 @@ const char* dddm_strerror(int status);
  * their row sums would mix; the TMA-staged kernel then reports NaN sums after a bounded wait.
  * ------------------------------------------------------------------------------------------ */
 size_t dddm_energy_workspace_bytes(int B, int m);
+/* Re-zero a workspace on `stream` (asynchronous).  Only needed after a launch that used it was aborted (a sticky CUDA
+ * error, a killed process sharing the allocation): its ticket / row slots may then be left half-written. */
+int dddm_energy_workspace_reset(void* workspace, int B, int m, dddm_stream_t stream);
 /* number of floats per row in the saved-distance buffer of the split fwd/bwd pair: m + m(m-1)/2 */
 size_t dddm_energy_dist_per_row(int m);
 

@@ -500,6 +500,38 @@ def test_finish_protocols_bit_identical(dev):
             _cabi.set_tuning(k, 0)
 
 
+def test_workspace_reset_recovers_a_corrupted_workspace(dev):
+    """A workspace left half-written by an aborted launch may give wrong sums (never a hang); dddm_energy_workspace_reset makes it usable again
+    (both cross-row protocols share the slots: TMA-staged kernel = polled slots, register kernel = arrival ticket)."""
+    from ddm_b200 import _cabi
+
+    L = _cabi.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for B, m, D in ((64, 8, 3072), (9, 4, 6)):  # TMA-staged kernel / register-resident kernel (unaligned rows)
+        xh, x0 = _synthetic(B, m, D, "late", seed=5)
+        xh, x0 = xh.to(dev), x0.to(dev)
+        w = torch.full((1,), 0.5 * B, device=dev)
+        out, grad = torch.zeros(4, device=dev), torch.empty_like(xh)
+        ws = torch.zeros(L.dddm_energy_workspace_bytes(B, m), dtype=torch.uint8, device=dev)
+
+        def run():
+            out.zero_()
+            _cabi.check(L.dddm_energy_fused_f32(xh.data_ptr(), x0.data_ptr(), w.data_ptr(), 1.0 / B, grad.data_ptr(), out.data_ptr(),
+                                                ws.data_ptr(), B, m, D, 0.1, 1.0, stream))
+            torch.cuda.synchronize()
+            return out.clone()
+
+        good = run()
+        assert torch.equal(run(), good)
+        ws[16:].view(torch.int64)[: B // 2] = -(2**62)  # half of the rows look "arrived" (bit 63) with garbage sums
+        ws[:4].view(torch.int32)[0] = 3                   # and the ticket is left in the middle of a count
+        run()  # sums may be anything (which protocol step sees the garbage first is a race) — but the launch must end
+        _cabi.check(L.dddm_energy_workspace_reset(ws.data_ptr(), B, m, stream))
+        assert torch.equal(run(), good)
+        assert torch.equal(run(), good)
+    assert L.dddm_energy_workspace_reset(None, 4, 8, stream) == -1
+
+
 @pytest.mark.parametrize("m", [16, 24, 32])
 def test_blocked_kernel_plans_agree(dev, m):
     """m = 16 / 32: the blocked packed-fp32 kernel (variant 4) under every cluster size and thread count, and the
