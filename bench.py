@@ -267,6 +267,23 @@ def run_aux(args, dev, world, rank, L, peak) -> dict:
     aux["k1_bf16_x0f32"] = k1_block("bf16", x0_f32=True)
     torch.cuda.empty_cache()
 
+    # -- the same launch with its inputs L2-RESIDENT (2 rotating sets = 53 MB < L2): what it costs inside a training step, where
+    #    the backbone has just written the draws and the backward pass reads the gradient back from L2.  NOT a roofline figure.
+    def k1_warm(dtype_name, x0_f32=False):
+        kb = K1Bench(L, dev, dtype_name, rank, world, 1, args.no_graph, nsets=2, x0_f32=x0_f32)
+        K = 480
+        with torch.cuda.stream(kb.stream):
+            kb.run_serial(K)
+            kb.stream.synchronize()
+            ser, _ = kb.timed(kb.run_serial, K, 5)
+        return 1e6 * ser / K
+
+    aux["k1_l2_resident"] = {"f32_us_per_launch": k1_warm("f32"), "bf16_us_per_launch": k1_warm("bf16"),
+                             "bf16_x0f32_us_per_launch": k1_warm("bf16", x0_f32=True),
+                             "note": "one stream, 2 rotating sets (inputs and gradient stay in the 126 MB L2): the cost of the loss "
+                                     "launch inside a training step; the headline uses HBM-cold inputs (40 sets)"}
+    torch.cuda.empty_cache()
+
     # -- BASELINE config 3 at its tensor-core point: m = 32, bf16 — the tcgen05 kernel against the blocked packed-fp32 kernel
     def k1_m32(variant):
         _cabi.set_tuning("energy.variant", variant)
