@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Achieved HBM bandwidth of the elementwise kernels around the energy score at their BASELINE shapes (CUDA graph of
-back-to-back launches over rotating buffers larger than L2, CUDA events).  One JSON line per kernel."""
+back-to-back launches over rotating buffers larger than L2 — inputs AND outputs distinct per launch — CUDA events).
+One JSON line per kernel.  `bench.py` (`aux.elementwise`) runs the same measurement with 8x L2 of rotating sets."""
 import json
 import os
 import sys
@@ -22,11 +23,11 @@ def bench(name, make, call, nbytes, nsets):
             call(s)
     stream.synchronize()
     g = torch.cuda.CUDAGraph()
-    reps = max(1, 200 // nsets)
+    reps = 1
+    keep = []  # the ops allocate their outputs: kept alive so that every launch writes its own, HBM-cold block
     with torch.cuda.graph(g, stream=stream):
-        for _ in range(reps):
-            for s in sets:
-                call(s)
+        for s in sets:
+            keep.append(call(s))
     ts = []
     with torch.cuda.stream(stream):
         g.replay()
