@@ -6,10 +6,32 @@
 // All are pure streaming kernels: 16-byte vector loads/stores, grids sized as a multiple of the
 // SM count, no shared-memory staging (nothing is reused).
 #include "common.cuh"
+#include "energy.cuh"  // launch_with_attrs (programmatic dependent launch)
 
 namespace dddm {
 
 static int num_sms() { return device_sm_count(); }  // per-device cache in api.cu
+
+// Every streaming kernel below starts with pdl_prologue(): launched with the PDL attribute (tuning().pdl, like K1) its CTAs
+// may become resident while the previous kernel of the stream drains, and wait here — before their first global access —
+// until that kernel has completed and its writes are visible.  Without the attribute both calls are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+}
+template <typename K, typename... Args>
+static int launch_streaming(K kernel, dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    return launch_with_attrs(kernel, grid, block, 0, 1, stream, args...);  // counts the launch
+}
+// A/B on one box, back-to-back launches with HBM-cold inputs and outputs (profiles/r02/elementwise_pdl_ab.log):
+// K2c 7.51 / 7.67 -> 7.34 / 7.35 us and K3 9.86 / 9.91 -> 9.44 / 9.26 us with the attribute, but K2 (almost only stores:
+// 3 MB in, 12.6 MB out) 3.99 / 4.22 -> 4.69 / 4.78 us, so K2 keeps the plain launch.
+template <typename K, typename... Args>
+static int launch_plain(K kernel, dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    kernel<<<grid, block, 0, stream>>>(args...);
+    count_launch();
+    return (int)cudaGetLastError();
+}
 
 template <typename T>
 static bool aligned16(const T* p) {
@@ -60,12 +82,8 @@ static int forward_marginal_expand(const T* x0, const float* t, const T* eps, T*
     if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
     if (B > 65535) return DDDM_ERR_BAD_SHAPE;
     dim3 grid((unsigned)tiles, (unsigned)B);
-    if (vec)
-        forward_marginal_expand_kernel<T, V><<<grid, threads, 0, stream>>>(x0, t, eps, xt, xt_rep, m, D);
-    else
-        forward_marginal_expand_kernel<T, 1><<<grid, threads, 0, stream>>>(x0, t, eps, xt, xt_rep, m, D);
-    count_launch();
-    return (int)cudaGetLastError();
+    return vec ? launch_plain(forward_marginal_expand_kernel<T, V>, grid, dim3(threads), stream, x0, t, eps, xt, xt_rep, m, D)
+               : launch_plain(forward_marginal_expand_kernel<T, 1>, grid, dim3(threads), stream, x0, t, eps, xt, xt_rep, m, D);
 }
 
 // ---- K2c -----------------------------------------------------------------------------------
@@ -95,13 +113,14 @@ __device__ __forceinline__ void load4(const TI* src, float (&v)[4]) {
 }
 
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)  // 3 CTAs per SM: the B x 3 CTAs of the CIFAR shape are resident in one wave
 forward_marginal_concat_kernel(const TI* __restrict__ x0, const float* __restrict__ t, const TI* __restrict__ eps,
                                const TI* __restrict__ xi, TO* __restrict__ x6, TI* __restrict__ x0_tok, int m, int C, int H,
                                int W, int patch) {
     const long D = (long)C * H * W;
     const long nquad = D / 4;
     const int b = blockIdx.y;
+    pdl_prologue();
     const float tb = t[b];
     const float ab = 1.0f - tb;
     const TI* x0r = x0 + (long)b * D;
@@ -113,12 +132,21 @@ forward_marginal_concat_kernel(const TI* __restrict__ x0, const float* __restric
         load4<TI>(er + e, n);
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[k] = __fadd_rn(__fmul_rn(ab, a[k]), __fmul_rn(tb, n[k]));  // no FMA: matches eager
-        for (int i = 0; i < m; ++i) {
-            TO* dst = x6 + ((long)b * m + i) * 2 * D;
-            store4<TI, TO>(dst + e, o);
-            float z[4];
-            load4<TI>(xi + ((long)b * m + i) * D + e, z);
-            store4<TI, TO>(dst + D + e, z);
+        // xi of up to 8 draws is requested before the first of them is stored: a thread owns ONE quad, so with one
+        // load -> store round trip per draw the launch was a chain of m HBM latencies (8.35 us for 29.9 MB at m = 8)
+        constexpr int U = 8;
+        for (int i0 = 0; i0 < m; i0 += U) {
+            float z[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u < m) load4<TI>(xi + ((long)b * m + i0 + u) * D + e, z[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u < m) {
+                    TO* dst = x6 + ((long)b * m + i0 + u) * 2 * D;
+                    store4<TI, TO>(dst + e, o);
+                    store4<TI, TO>(dst + D + e, z[u]);
+                }
         }
         if (x0_tok != nullptr) {
             const int x = (int)(e % W), y = (int)((e / W) % H), c = (int)(e / ((long)W * H));
@@ -144,10 +172,8 @@ static int forward_marginal_concat(const TI* x0, const float* t, const TI* eps, 
     long tiles = (nquad + threads - 1) / threads;
     const long max_tiles = ((long)num_sms() * 8 + B - 1) / B;
     if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
-    forward_marginal_concat_kernel<TI, TO><<<dim3((unsigned)tiles, (unsigned)B), threads, 0, stream>>>(
-        x0, t, eps, xi, x6, x0_tok, m, C, H, W, patch);
-    count_launch();
-    return (int)cudaGetLastError();
+    return launch_streaming(forward_marginal_concat_kernel<TI, TO>, dim3((unsigned)tiles, (unsigned)B), dim3(threads), stream,
+                            x0, t, eps, xi, x6, x0_tok, m, C, H, W, patch);
 }
 
 // ---- K4 ------------------------------------------------------------------------------------
@@ -210,6 +236,7 @@ bridge_step_kernel(T* __restrict__ x_out, const T* __restrict__ x, const T* __re
                    int st_is_vector, float e2, float ome2, T* __restrict__ mu_out, float* __restrict__ std_out, long N,
                    long D) {
     const long nvec = D / VEC;
+    pdl_prologue();
     for (long n = blockIdx.y; n < N; n += gridDim.y) {
         const BridgeCoef c = st_is_vector ? bridge_coef(s[n], t[n], e2, ome2) : bridge_coef(s[0], t[0], e2, ome2);
         if (std_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && (st_is_vector || n == 0)) std_out[n] = c.std;
@@ -243,6 +270,7 @@ __global__ void __launch_bounds__(256)
 bridge_step_flat_kernel(T* __restrict__ x_out, const T* __restrict__ x, const T* __restrict__ xhat0,
                         const T* __restrict__ z, const float* __restrict__ s, const float* __restrict__ t, float e2,
                         float ome2, long nvec) {
+    pdl_prologue();
     const BridgeCoef c = bridge_coef(s[0], t[0], e2, ome2);
     const long stride = (long)gridDim.x * blockDim.x;
     for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
@@ -289,9 +317,8 @@ static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const f
         long blocks = (total + 256L * kUnroll - 1) / (256L * kUnroll);
         const long cap = (long)num_sms() * 16;
         if (blocks > cap) blocks = cap;
-        bridge_step_flat_kernel<T, V, kUnroll><<<(unsigned)blocks, 256, 0, stream>>>(x_out, x, xhat0, z, s, t, e2, ome2, total);
-        count_launch();
-        return (int)cudaGetLastError();
+        return launch_streaming(bridge_step_flat_kernel<T, V, kUnroll>, dim3((unsigned)blocks), dim3(256), stream, x_out, x, xhat0, z,
+                                s, t, e2, ome2, total);
     }
     const long nvec = vec ? D / V : D;
     const int threads = nvec >= 256 ? 256 : (int)((nvec + 31) / 32 * 32);
@@ -300,14 +327,10 @@ static int bridge_step(T* x_out, const T* x, const T* xhat0, const T* z, const f
     const long max_tiles = ((long)num_sms() * 8 + rows - 1) / rows;
     if (tiles > max_tiles) tiles = max_tiles < 1 ? 1 : max_tiles;
     dim3 grid((unsigned)tiles, (unsigned)rows);
-    if (vec)
-        bridge_step_kernel<T, V><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
-                                                                mu_out, std_out, N, D);
-    else
-        bridge_step_kernel<T, 1><<<grid, threads, 0, stream>>>(x_out, x, xhat0, z, s, t, st_is_vector, e2, ome2,
-                                                                mu_out, std_out, N, D);
-    count_launch();
-    return (int)cudaGetLastError();
+    return vec ? launch_streaming(bridge_step_kernel<T, V>, grid, dim3(threads), stream, x_out, x, xhat0, z, s, t, st_is_vector, e2,
+                                  ome2, mu_out, std_out, N, D)
+               : launch_streaming(bridge_step_kernel<T, 1>, grid, dim3(threads), stream, x_out, x, xhat0, z, s, t, st_is_vector, e2,
+                                  ome2, mu_out, std_out, N, D);
 }
 
 // ---- K3 with the Gaussian draws fused in (dddm/sampling.py:27,30) ----------------------------------------------

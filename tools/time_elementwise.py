@@ -9,13 +9,25 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from ddm_b200 import ops
+import argparse
+
+from ddm_b200 import _cabi, ops
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the streaming kernels (tuning energy.pdl)")
+ap.add_argument("--only", default="", help="comma-separated prefixes of the kernels to time (K2,K2c,K3,K4,K6); default all")
+a = ap.parse_args()
+_cabi.set_tuning("energy.pdl", a.pdl)
+ONLY = [p_ for p_ in a.only.split(",") if p_]
 
 dev = torch.device("cuda:0")
 PEAK = 6452.5
 
 
 def bench(name, make, call, nbytes, nsets):
+    if ONLY and name.split()[0] not in ONLY:
+        return
+    nsets = max(nsets, -(-8 * 126 * 2**20 // nbytes)) if nbytes > 2**20 else nsets  # 8 x L2 of rotating sets
     sets = [make(i) for i in range(nsets)]
     stream = torch.cuda.Stream(dev)
     with torch.cuda.stream(stream):
@@ -39,7 +51,7 @@ def bench(name, make, call, nbytes, nsets):
             e1.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e3 / (reps * nsets))
     us = sorted(ts)[2]
-    print(json.dumps({"kernel": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
+    print(json.dumps({"pdl": a.pdl, "kernel": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
                       "GBps": round(nbytes / us / 1e3, 1), "frac_of_measured_hbm_peak": round(nbytes / us / 1e3 / PEAK, 3)}),
           flush=True)
 
