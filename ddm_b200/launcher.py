@@ -531,6 +531,49 @@ def dp_parity(args, dev, world, batch_per_rank: int = 16) -> dict:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
 
 
+def build_train_loader(args, world: int, rank: int, dataset=None):
+    """The real-CIFAR input pipeline of the reference (`dddm/data.py:195-247`, called from `train_cifar10_dit.py:104-113`):
+    reflect-padded random crop of 32 + horizontal flip unless `--no-augment`, resize when `--image-size` is not 32, `ToTensor`,
+    normalisation to [-1, 1]; shuffled, `drop_last=True`, `--workers` workers, pinned memory.  Differences, both forced by one
+    process per GPU: every rank reads its own `DistributedSampler` shard (re-seeded per epoch by the caller) and `args.batch` is
+    the PER-GPU batch (`resolve_batch`).  The dataset is never downloaded (no network on the training boxes): `--data-dir` must
+    hold `cifar-10-batches-py`.  `dataset` replaces `datasets.CIFAR10` (any dataset of (PIL image, label) pairs: the CPU
+    test)."""
+    try:
+        from torchvision import datasets, transforms
+    except ImportError as exc:
+        raise RuntimeError("torchvision is needed for CIFAR-10; pass --synthetic to train on random images") from exc
+    tfms = []
+    if not args.no_augment:
+        tfms += [transforms.RandomCrop(32, padding=4, padding_mode="reflect"), transforms.RandomHorizontalFlip()]
+    if args.image_size != 32:
+        tfms.append(transforms.Resize(args.image_size))
+    tfms += [transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))]
+    tf = transforms.Compose(tfms)
+    if dataset is None:
+        ds = datasets.CIFAR10(args.data_dir, train=True, download=False, transform=tf)
+    else:
+        ds = _Transformed(dataset, tf)
+    sampler = (torch.utils.data.distributed.DistributedSampler(ds, num_replicas=world, rank=rank, shuffle=True, seed=args.seed)
+               if world > 1 else None)
+    return torch.utils.data.DataLoader(ds, batch_size=args.batch, sampler=sampler, shuffle=sampler is None,
+                                       num_workers=args.workers, pin_memory=torch.cuda.is_available(), drop_last=True)
+
+
+class _Transformed(torch.utils.data.Dataset):
+    """(image, label) dataset with the training transform applied on access, like `datasets.CIFAR10(transform=...)`."""
+
+    def __init__(self, base, transform):
+        self.base, self.transform = base, transform
+
+    def __len__(self):
+        return len(self.base)
+
+    def __getitem__(self, i):
+        img, label = self.base[i]
+        return self.transform(img), label
+
+
 def main(argv=None) -> None:
     parser = build_parser()
     args = parser.parse_args(argv)
@@ -544,18 +587,7 @@ def main(argv=None) -> None:
     os.makedirs(args.out, exist_ok=True)
     tr = Trainer(args, dev, world)
 
-    loader = None
-    if not args.synthetic:
-        try:
-            from torchvision import datasets, transforms
-        except ImportError as exc:
-            raise RuntimeError("torchvision is needed for CIFAR-10; pass --synthetic to train on random images") from exc
-        aug = [] if args.no_augment else [transforms.RandomCrop(args.image_size, padding=4), transforms.RandomHorizontalFlip()]
-        tf = transforms.Compose(aug + [transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
-        ds = datasets.CIFAR10(args.data_dir, train=True, download=False, transform=tf)
-        sampler = torch.utils.data.distributed.DistributedSampler(ds) if world > 1 else None
-        loader = torch.utils.data.DataLoader(ds, batch_size=args.batch, sampler=sampler, shuffle=sampler is None,
-                                             num_workers=args.workers, pin_memory=True, drop_last=True)
+    loader = None if args.synthetic else build_train_loader(args, world, rank)
 
     history, gstep = [], 0
     for epoch in range(1, args.epochs + 1):

@@ -93,6 +93,45 @@ def test_launcher_flags_and_yaml_overlay(tmp_path):
         launcher.apply_yaml(p, a)
 
 
+def test_real_cifar_loader_branch_on_a_fake_image_dataset():
+    """`launcher.build_train_loader` — the reference's CIFAR pipeline (dddm/data.py:195-247: reflect-padded crop + flip, ToTensor,
+    [-1, 1] normalisation, shuffled, drop_last) with one DistributedSampler shard per rank — on (PIL image, label) pairs."""
+    from PIL import Image
+
+    from ddm_b200 import launcher
+
+    g = np.random.default_rng(0)
+    imgs = [(Image.fromarray(g.integers(0, 256, (32, 32, 3), dtype=np.uint8)), int(i % 10)) for i in range(50)]
+    p = launcher.build_parser()
+
+    a = p.parse_args(["--batch", "8", "--workers", "0", "--no-augment"])
+    batches = list(launcher.build_train_loader(a, 1, 0, dataset=imgs))
+    assert len(batches) == 6 and all(x.shape == (8, 3, 32, 32) and x.dtype == torch.float32 for x, _ in batches)  # drop_last
+    x = torch.cat([x for x, _ in batches])
+    assert -1.0 <= float(x.min()) and float(x.max()) <= 1.0 and float(x.min()) < -0.9 and float(x.max()) > 0.9
+    # without augmentation every batch row is one of the images, normalised as (v / 255 - 0.5) / 0.5
+    want = torch.stack([torch.from_numpy(np.array(im)).permute(2, 0, 1).float().div(255).sub(0.5).div(0.5) for im, _ in imgs])
+    assert all(bool((want == row).flatten(1).all(dim=1).any()) for row in x)
+
+    # augmentation keeps shape and range; a non-32 image size resizes after the crop
+    a = p.parse_args(["--batch", "8", "--workers", "0", "--image-size", "16"])
+    xb, _ = next(iter(launcher.build_train_loader(a, 1, 0, dataset=imgs)))
+    assert xb.shape == (8, 3, 16, 16) and float(xb.abs().max()) <= 1.0
+
+    # two ranks: disjoint shards that cover the dataset (DistributedSampler pads 50 -> 2 x 25), re-shuffled per epoch
+    a = p.parse_args(["--batch", "5", "--workers", "0", "--no-augment", "--seed", "3"])
+    seen = []
+    for rank in (0, 1):
+        ld = launcher.build_train_loader(a, 2, rank, dataset=imgs)
+        ld.sampler.set_epoch(1)
+        idx = list(ld.sampler)
+        assert len(idx) == 25 and len(list(ld)) == 5
+        seen.append(set(idx))
+    assert seen[0].isdisjoint(seen[1]) and seen[0] | seen[1] == set(range(50))
+    ld.sampler.set_epoch(2)
+    assert list(ld.sampler) != idx
+
+
 def _tiny_loss(model, x):
     y = model(x)
     loss = (y * y).mean() + 0.1 * y.abs().mean()
