@@ -129,7 +129,7 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
         }
     }
     if (p.x0_f32) {  // bf16 draws + fp32 x0: the TMA-staged kernel is the only one with a mixed tile
-        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 2);
+        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 2, p.B);
         if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
         return DDDM_ERR_UNSUPPORTED;
     }
@@ -139,7 +139,7 @@ static int run_forward(EnergyParams& p, void* workspace, cudaStream_t stream) {
         if (variant == 5) return DDDM_ERR_UNSUPPORTED;
     }
     if (variant == 0 || variant == 3) {
-        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al);
+        SmemPlan sp = plan_smem(p.m, p.D, (int)sizeof(T), al, 1, p.B);
         if (sp.ok) return launch_energy_smem<T>(p, sp, stream);
         if (variant == 3) return DDDM_ERR_UNSUPPORTED;
     }
@@ -236,7 +236,7 @@ static int energy_terms_bwd(const T* xhat, const T* x0, const float* dist, const
     }
     if (tuning().variant == 0 || tuning().variant == 3) {
         // TMA-staged packed-fp32 kernel in backward mode (pass 2 only, coefficients from the saved distances)
-        SmemPlan sp = plan_smem(m, D, (int)sizeof(T), al);
+        SmemPlan sp = plan_smem(m, D, (int)sizeof(T), al, 1, B);
         if (sp.ok) {
             p.mode = kModeBwd;
             p.trace = static_cast<unsigned long long*>(tuning().trace);
@@ -426,7 +426,7 @@ int dddm_energy_describe(int B, int m, int D, int dtype, char* buf, int buflen) 
         if (variant == 5) return snprintf(buf, buflen, "unsupported");
     }
     if (variant == 0 || variant == 3) {
-        SmemPlan sp = plan_smem(m, D, es, al);
+        SmemPlan sp = plan_smem(m, D, es, al, 1, B);
         if (sp.ok) {
             const bool ldgsts = tuning().loader == 2;
             return snprintf(buf, buflen, "smem<%s,M=%d> %s f32x2 cluster=%d threads=%d slab_vecs=%d chunk_vecs=%d smem=%zu",

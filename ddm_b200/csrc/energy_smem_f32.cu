@@ -3,7 +3,7 @@
 
 namespace dddm {
 
-SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows) {
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows, int B) {
     SmemPlan s{};
     s.ok = false;
     const int vecw = 16 / elem_size;
@@ -16,6 +16,15 @@ SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows) {
         // (measured on B200: fewer, fatter CTAs beat D-split clusters — no DSMEM round trip)
         cluster = 1;
         while (cluster < 8 && (size_t)(m + x0_rows) * ((nvec + cluster - 1) / cluster) * 16 > 112 * 1024) cluster *= 2;
+        // Small minibatches (the reference's CIFAR recipe is 64 rows per GPU on 4 GPUs, 32 on 8): with fewer rows than half
+        // the SMs a row is split along D so that B x cluster CTAs still fit one CTA per SM — each SM then pulls and writes
+        // 1/cluster of a row (profiles/r02/k1_small_batch_clusters.log, one launch, fp32 / bf16: B = 32 6.81 -> 5.89 /
+        // 6.80 -> 5.75 us with 4 CTAs per row, B = 64 7.36 -> 7.11 / 7.10 -> 6.47 us with 2; B = 96 is slower split).
+        // Slabs stay >= 96 vectors per row: bulk copies under ~1.5 KB are bound per request.
+        if (B > 0 && t.threads <= kSmemMaxThreads) {  // (the opt-in 8-warp build owns whole rows)
+            const long sms = device_sm_count();
+            while (cluster < 4 && (long)B * cluster * 2 <= sms && nvec / (cluster * 2) >= 96) cluster *= 2;
+        }
     }
     const long slab = (nvec + cluster - 1) / cluster;
     const size_t smem = (size_t)(m + x0_rows) * slab * 16;  // x0_rows = 2: fp32 x0 next to bf16 draws (mixed entry)

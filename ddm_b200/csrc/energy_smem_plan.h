@@ -10,7 +10,8 @@ struct SmemPlan {
     int cluster, threads, slab_vecs, chunk_vecs;
     size_t smem_bytes;
 };
-SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows = 1);
+// B > 0: rows of the launch (small minibatches are split along D so that B x cluster CTAs cover the SMs); 0 = not known
+SmemPlan plan_smem(int m, int D, int elem_size, bool aligned16, int x0_rows = 1, int B = 0);
 template <typename T>
 int launch_energy_smem(const EnergyParams& p, const SmemPlan& plan, cudaStream_t stream);
 // single-wave register-resident variant (energy_wave.cuh)

@@ -61,6 +61,12 @@ def test_kernel_plans(cabi):
     try:
         assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> tma-bulk f32x2")
         assert cabi.describe_energy(128, 8, 3072, "bf16").startswith("smem<bf16,M=8>")
+        # small minibatches are split along D so that B x cluster CTAs cover the SMs (one CTA per SM at most)
+        assert "cluster=1 " in cabi.describe_energy(128, 8, 3072) and "cluster=1 " in cabi.describe_energy(96, 8, 3072)
+        assert "cluster=2 threads=128 slab_vecs=384" in cabi.describe_energy(64, 8, 3072)
+        assert "cluster=4 threads=128 slab_vecs=192" in cabi.describe_energy(32, 8, 3072)
+        assert "cluster=4 threads=96 slab_vecs=96" in cabi.describe_energy(16, 8, 3072, "bf16")
+        assert "cluster=1 " in cabi.describe_energy(16, 8, 512)  # narrow rows stay whole
         cabi.set_tuning("energy.loader", 2)
         assert cabi.describe_energy(128, 8, 3072).startswith("smem<f32,M=8> cp.async f32x2")
         cabi.set_tuning("energy.loader", 0)
