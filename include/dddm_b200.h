@@ -281,7 +281,8 @@ int dddm_rbf_kernel_sum_f32(const float* G, long ldg, const float* a2, const flo
 /* ------------------------------------------------------------------------------------------
  * Tuning / introspection (benchmarks and tests; never needed for correctness).
  *   keys: "energy.variant" (0 = auto, 1 = register-resident, 2 = chunked shared-memory tile for any m,
- *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto),
+ *         3 = TMA-staged packed-fp32 kernel for m <= 8, 4 = blocked packed-fp32 kernel for m = 16, 32), "energy.cluster" (CTAs per row, 0 = auto: whole rows, split along D only for rows too wide for one tile and — variant 3 — for
+ *         minibatches of fewer rows than half the SMs),
  *         "energy.threads" (threads per CTA of variant 3, 0 = auto), "energy.nv" (16-byte vectors per
  *         thread of variant 1, 0 = auto), "energy.pdl" (programmatic dependent launch, default 1), "energy.ctas" (experiment),
  *         "energy.variant" = 5 (single-wave register-resident kernel for m <= 8: "energy.threads" 128/256/384 x "energy.nv"
