@@ -5,6 +5,8 @@
 //   scale-in-place (hand-off of the pre-multiplied gradient of K1 to autograd)
 // All are pure streaming kernels: 16-byte vector loads/stores, grids sized as a multiple of the
 // SM count, no shared-memory staging (nothing is reused).
+#include <type_traits>
+
 #include "common.cuh"
 #include "energy.cuh"  // launch_with_attrs (programmatic dependent launch)
 
@@ -135,23 +137,32 @@ forward_marginal_concat_kernel(const TI* __restrict__ x0, const float* __restric
         // xi of up to 8 draws is requested before the first of them is stored: a thread owns ONE quad, so with one
         // load -> store round trip per draw the launch was a chain of m HBM latencies (8.35 us for 29.9 MB at m = 8)
         constexpr int U = 8;
-        for (int i0 = 0; i0 < m; i0 += U) {
+        auto draws = [&](int i0, auto full_tag) {  // FULL: all U draws exist (m = 8: no guards, no branches)
+            constexpr bool FULL = decltype(full_tag)::value;
+            const TI* src = xi + ((long)b * m + i0) * D + e;
+            TO* dst = x6 + ((long)b * m + i0) * 2 * D + e;
             float z[U][4];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i0 + u < m) load4<TI>(xi + ((long)b * m + i0 + u) * D + e, z[u]);
+                if (FULL || i0 + u < m) load4<TI>(src + (long)u * D, z[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i0 + u < m) {
-                    TO* dst = x6 + ((long)b * m + i0 + u) * 2 * D;
-                    store4<TI, TO>(dst + e, o);
-                    store4<TI, TO>(dst + D + e, z[u]);
+                if (FULL || i0 + u < m) {
+                    store4<TI, TO>(dst + (long)u * 2 * D, o);
+                    store4<TI, TO>(dst + (long)u * 2 * D + D, z[u]);
                 }
-        }
+        };
+        int i0 = 0;
+        for (; i0 + U <= m; i0 += U) draws(i0, std::true_type{});
+        if (i0 < m) draws(i0, std::false_type{});
         if (x0_tok != nullptr) {
-            const int x = (int)(e % W), y = (int)((e / W) % H), c = (int)(e / ((long)W * H));
-            const int gx = x / patch, px = x - gx * patch, gy = y / patch, py = y - gy * patch;
-            const long tok = (((long)gy * (W / patch) + gx) * C + c) * patch * patch + (long)py * patch + px;
+            // pixel (c, y, x) -> token ((gy, gx), c, py, px) in 32-bit unsigned arithmetic (D < 2^31 is checked by the
+            // launcher): the 64-bit divisions this used to be were more than half of the kernel's instructions
+            const unsigned ue = (unsigned)e, uW = (unsigned)W, uH = (unsigned)H, up = (unsigned)patch;
+            const unsigned row = ue / uW, x = ue - row * uW;
+            const unsigned c = row / uH, y = row - c * uH;
+            const unsigned gx = x / up, px = x - gx * up, gy = y / up, py = y - gy * up;
+            const unsigned tok = ((gy * (uW / up) + gx) * (unsigned)C + c) * up * up + py * up + px;
             store4<TI, TI>(x0_tok + (long)b * D + tok, a);
         }
     }
@@ -161,7 +172,7 @@ template <typename TI, typename TO>
 static int forward_marginal_concat(const TI* x0, const float* t, const TI* eps, const TI* xi, TO* x6, TI* x0_tok, int B,
                                    int m, int C, int H, int W, int patch, cudaStream_t stream) {
     if (!x0 || !t || !eps || !xi || !x6) return DDDM_ERR_NULL_POINTER;
-    if (B < 0 || m < 1 || C < 1 || H < 1 || W < 1 || B > 65535) return DDDM_ERR_BAD_SHAPE;
+    if (B < 0 || m < 1 || C < 1 || H < 1 || W < 1 || B > 65535 || (long)C * H * W >= (1L << 31)) return DDDM_ERR_BAD_SHAPE;
     if (W % 4 != 0) return DDDM_ERR_UNSUPPORTED;
     if (x0_tok && (patch < 4 || patch % 4 != 0 || W % patch != 0 || H % patch != 0)) return DDDM_ERR_BAD_SHAPE;
     if (!aligned16(x0) || !aligned16(eps) || !aligned16(xi) || !aligned16(x6) || (x0_tok && !aligned16(x0_tok)))

@@ -319,7 +319,8 @@ def test_forward_marginal_concat_bit_exact(dev):
     from oracle import torch_port
 
     gen = torch.Generator().manual_seed(3)
-    for B, m, C, H, W, p in ((5, 3, 3, 32, 32, 4), (2, 8, 3, 16, 24, 8), (3, 2, 1, 8, 8, 4)):
+    # m = 8: one unguarded block of 8 draws; m = 11: that block + a guarded remainder; m = 2, 3: the guarded block alone
+    for B, m, C, H, W, p in ((5, 3, 3, 32, 32, 4), (2, 8, 3, 16, 24, 8), (3, 2, 1, 8, 8, 4), (2, 11, 3, 8, 8, 4)):
         x0 = (torch.rand(B, C, H, W, generator=gen) * 2 - 1)
         eps, xi, t = torch.randn(B, C, H, W, generator=gen), torch.randn(B, m, C, H, W, generator=gen), torch.rand(B, generator=gen)
         xt = torch_port.forward_marginal(x0, t, eps)  # CPU eager fp32 = the reference's arithmetic
